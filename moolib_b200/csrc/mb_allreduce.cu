@@ -1,0 +1,825 @@
+// HP-A: gradient allreduce over NVLink/NVSwitch peer memory -- no NCCL, no serialisation, no host staging.
+//
+//   K-A1  ar_stage_kernel    : pack (=) or accumulate (+=) a tensor list into the rank's symmetric staging buffer and
+//                              optionally zero the sources, one launch for the whole list.
+//   K-A2  ar_oneshot_kernel  : per-block flag barrier with every peer (st.release.sys into the peer's flag row /
+//                              ld.acquire.sys on the local row), then each rank pulls all peers' staging with 16 B P2P
+//                              loads, sums in ascending rank order in fp32, multiplies by 1.0f/sum(num_gradients) and
+//                              scatters straight into the destination tensors.  (N-1)*S bytes in per GPU, one barrier.
+//         ar_twoshot_kernel  : reduce-scatter by P2P loads (rank r reduces slice r), all-gather by P2P stores into
+//                              every peer's staging, second flag barrier, local scatter.  2(N-1)/N*S per direction.
+// Both give bit-identical results on every rank and identical to each other (same summation order).
+//
+// Reference semantics being replaced: src/accumulator.cc:941-980 (stage), src/group.h:195-212 (add),
+// src/group.h:570-654,687-787 (tree reduce + share), src/accumulator.cc:425-452 (copy_ + mul_(1.0f/numGradients)).
+#include "mb_common.cuh"
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace mb {
+namespace {
+
+constexpr int kArThreads = 512;
+constexpr int kArMaxBlocks = 1024;
+constexpr int kArMaxTensors = 4096;
+constexpr uint32_t kHandleMagic = 0x4d423230u;  // "MB20"
+
+struct TensorEnt {
+  uint64_t ptr;    // device address of the tensor's first float
+  uint64_t off;    // first float in the flat layout (multiple of 4)
+  uint64_t numel;  // floats
+};
+
+// Lives in device memory of its owner, mapped by every peer.  Zero-initialised.
+struct SyncBlock {
+  mb_ar_hdr hdr[2];                                 // [epoch parity], written by the owner before it signals
+  uint32_t flagsA[kArMaxBlocks][MB_AR_MAX_WORLD];   // [block][source rank] = epoch: "my data for this round is staged"
+  uint32_t flagsB[kArMaxBlocks][MB_AR_MAX_WORLD];   // two-shot: "my reduced slice is written to your staging"
+};
+
+struct HostResult {
+  mb_ar_hdr sum;
+  int32_t status;
+  uint32_t epoch;
+};
+
+struct HandleImpl {
+  uint32_t magic;
+  int32_t pid;
+  int32_t device;
+  int32_t rank;
+  uint64_t staging_ptr;
+  uint64_t sync_ptr;
+  uint64_t max_bytes;
+  int32_t nslots;
+  int32_t ipc_ok;
+  cudaIpcMemHandle_t h_staging;
+  cudaIpcMemHandle_t h_sync;
+};
+static_assert(sizeof(HandleImpl) <= MB_AR_HANDLE_BYTES, "mb_ar_handle too small");
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+}  // namespace mb
+
+struct mb_ar_ctx {
+  int rank = 0, world = 1, device = 0, nslots = 1;
+  uint64_t max_bytes = 0;  // per staging buffer, multiple of 16
+  float* staging = nullptr;          // nslots * 2 buffers (parity double-buffering, see mb_ar_allreduce)
+  mb::SyncBlock* sync = nullptr;
+  float* peer_staging[MB_AR_MAX_WORLD] = {};
+  mb::SyncBlock* peer_sync[MB_AR_MAX_WORLD] = {};
+  bool imported[MB_AR_MAX_WORLD] = {};
+  bool ipc_opened[MB_AR_MAX_WORLD] = {};
+  uint32_t epoch = 0;
+  int parity[MB_AR_MAX_SLOTS] = {};
+  mb::HostResult* result_host = nullptr;  // pinned + mapped, one per slot
+  mb::HostResult* result_dev = nullptr;
+  uint32_t* abort_host = nullptr;
+  uint32_t* abort_dev = nullptr;
+  mb::TensorEnt* tab_dev[2] = {nullptr, nullptr};  // 0: stage sources, 1: allreduce destinations
+  std::vector<mb::TensorEnt> tab_host[2];
+  std::mutex mu;
+};
+
+namespace mb {
+namespace {
+
+struct ArParams {
+  float* stage[MB_AR_MAX_WORLD];     // every rank's staging buffer for this slot/parity ([rank] = own)
+  SyncBlock* sync[MB_AR_MAX_WORLD];  // every rank's sync block
+  const TensorEnt* dst_tab;
+  uint32_t ntensors;
+  uint32_t epoch;
+  uint64_t total_vec;  // flat length in float4 units
+  uint64_t slice_vec;  // two-shot: ceil(total_vec / world)
+  mb_ar_hdr my_hdr;
+  int32_t rank;
+  int32_t world;
+  int32_t scale;
+  int32_t pad_;
+  HostResult* result;
+  const uint32_t* abort_flag;
+  uint64_t timeout_ns;
+};
+
+struct StageParams {
+  float* staging;
+  const TensorEnt* tab;
+  uint32_t ntensors;
+  int32_t accumulate;
+  int32_t zero_src;
+  uint64_t total_vec;
+};
+
+// ---- flat layout <-> tensor list ---------------------------------------------------------------------------------
+
+// s_off[i] = first float4 of tensor i in the flat layout.  Returns the tensor that owns float4 index v.
+__device__ __forceinline__ uint32_t find_tensor(const uint32_t* s_off, uint32_t n, uint32_t v) {
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (s_off[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void load_offsets(uint32_t* s_off, const TensorEnt* tab, uint32_t n) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_off[i] = (uint32_t)(tab[i].off >> 2);
+}
+
+__device__ __forceinline__ void scatter_vec(const TensorEnt* tab, const uint32_t* s_off, uint32_t n, uint64_t v,
+                                            const float4& r) {
+  const uint32_t t = find_tensor(s_off, n, (uint32_t)v);
+  const TensorEnt e = tab[t];
+  const uint64_t within = v * 4 - e.off;
+  if (within >= e.numel) return;  // padding-only vector (cannot happen for non-empty tensors, kept for safety)
+  float* d = reinterpret_cast<float*>(e.ptr) + within;
+  const uint64_t valid = e.numel - within;
+  if (valid >= 4 && (reinterpret_cast<uintptr_t>(d) & 15u) == 0) {
+    st_f4(d, r);
+  } else {
+    d[0] = r.x;
+    if (valid > 1) d[1] = r.y;
+    if (valid > 2) d[2] = r.z;
+    if (valid > 3) d[3] = r.w;
+  }
+}
+
+// ---- K-A1 --------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kArThreads) ar_stage_kernel(const __grid_constant__ StageParams p) {
+  __shared__ uint32_t s_off[kArMaxTensors];
+  load_offsets(s_off, p.tab, p.ntensors);
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * kArThreads;
+  for (uint64_t v = (uint64_t)blockIdx.x * kArThreads + threadIdx.x; v < p.total_vec; v += stride) {
+    const uint32_t t = find_tensor(s_off, p.ntensors, (uint32_t)v);
+    const TensorEnt e = p.tab[t];
+    const uint64_t within = v * 4 - e.off;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (within < e.numel) {
+      float* s = reinterpret_cast<float*>(e.ptr) + within;
+      const uint64_t valid = e.numel - within;
+      const bool vec = valid >= 4 && (reinterpret_cast<uintptr_t>(s) & 15u) == 0;
+      if (vec) {
+        g = *reinterpret_cast<const float4*>(s);
+      } else {
+        g.x = s[0];
+        if (valid > 1) g.y = s[1];
+        if (valid > 2) g.z = s[2];
+        if (valid > 3) g.w = s[3];
+      }
+      if (p.zero_src) {
+        if (vec) {
+          *reinterpret_cast<float4*>(s) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          s[0] = 0.f;
+          if (valid > 1) s[1] = 0.f;
+          if (valid > 2) s[2] = 0.f;
+          if (valid > 3) s[3] = 0.f;
+        }
+      }
+    }
+    float4* d = reinterpret_cast<float4*>(p.staging) + v;
+    if (p.accumulate) {
+      // staged += new  (src/accumulator.cc:975 targetGradients[i].add_(addGrads[i]))
+      const float4 a = *d;
+      g = make_float4(a.x + g.x, a.y + g.y, a.z + g.z, a.w + g.w);
+    }
+    *d = g;
+  }
+}
+
+// ---- barrier ----------------------------------------------------------------------------------------------------
+
+// Every block pairs with the same-numbered block on every peer.  Returns false on timeout / abort.
+__device__ __forceinline__ bool block_barrier(const ArParams& p, bool second) {
+  __syncthreads();  // the block's earlier writes happen-before the release below (cumulativity through bar.sync)
+  const int t = threadIdx.x;
+  int fail = 0;
+  if (t < p.world && t != p.rank) {
+    SyncBlock* peer = p.sync[t];
+    uint32_t* remote = second ? &peer->flagsB[blockIdx.x][p.rank] : &peer->flagsA[blockIdx.x][p.rank];
+    st_release_sys_u32(remote, p.epoch);
+    SyncBlock* me = p.sync[p.rank];
+    const uint32_t* local = second ? &me->flagsB[blockIdx.x][t] : &me->flagsA[blockIdx.x][t];
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while ((int32_t)(ld_acquire_sys_u32(local) - p.epoch) < 0) {
+      if ((++spins & 63u) == 0) {
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > p.timeout_ns || ld_volatile_u32(p.abort_flag) != 0) {
+          fail = 1;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+  }
+  return __syncthreads_or(fail) == 0;
+}
+
+__device__ __forceinline__ void report_failure(const ArParams& p) {
+  if (threadIdx.x == 0) {
+    p.result->status = MB_ETIMEOUT;
+    p.result->epoch = p.epoch;
+    __threadfence_system();
+  }
+}
+
+// After the first barrier: sum the peers' headers (u64 adds, src/group.h:209-211) and build the has-gradients mask.
+__device__ __forceinline__ void gather_headers(const ArParams& p, mb_ar_hdr* s_total, uint32_t* s_mask) {
+  if (threadIdx.x == 0) {
+    mb_ar_hdr tot = {0, 0, 0, 0};
+    uint32_t mask = 0;
+    for (int r = 0; r < p.world; ++r) {
+      uint64_t ng, ns, bs, hg;
+      if (r == p.rank) {
+        ng = p.my_hdr.num_gradients, ns = p.my_hdr.num_skipped, bs = p.my_hdr.batch_size, hg = p.my_hdr.has_grads;
+      } else {
+        const volatile mb_ar_hdr* ph = &p.sync[r]->hdr[p.epoch & 1u];
+        ng = ph->num_gradients, ns = ph->num_skipped, bs = ph->batch_size, hg = ph->has_grads;
+      }
+      tot.num_gradients += ng;
+      tot.num_skipped += ns;
+      tot.batch_size += bs;
+      if (hg) {
+        mask |= 1u << r;
+        tot.has_grads += 1;
+      }
+    }
+    *s_total = tot;
+    *s_mask = mask;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void publish_header(const ArParams& p) {
+  // every block writes the same value; the block's own release (block_barrier) orders it before its flag
+  if (threadIdx.x == 0) {
+    volatile mb_ar_hdr* h = &p.sync[p.rank]->hdr[p.epoch & 1u];
+    h->num_gradients = p.my_hdr.num_gradients;
+    h->num_skipped = p.my_hdr.num_skipped;
+    h->batch_size = p.my_hdr.batch_size;
+    h->has_grads = p.my_hdr.has_grads;
+  }
+}
+
+__device__ __forceinline__ float reduce_scale(const ArParams& p, const mb_ar_hdr& tot) {
+  // fp32 reciprocal then fp32 multiply, exactly as grad.mul_(1.0f / data.numGradients) (src/accumulator.cc:442)
+  if (!p.scale || tot.num_gradients == 0) return 1.0f;
+  return __fdiv_rn(1.0f, (float)tot.num_gradients);
+}
+
+__device__ __forceinline__ void add4(float4& a, const float4& b) {
+  a.x = __fadd_rn(a.x, b.x);
+  a.y = __fadd_rn(a.y, b.y);
+  a.z = __fadd_rn(a.z, b.z);
+  a.w = __fadd_rn(a.w, b.w);
+}
+
+// Sum of element v over the ranks in `mask`, ascending rank order, fp32.  Fast path (every rank contributes): all NR
+// loads are issued before the first add so NR x 16 B are in flight per thread.
+template <int NR>
+__device__ __forceinline__ float4 reduce_vec(float* const* stage, uint32_t mask, uint64_t v) {
+  if (mask == (1u << NR) - 1u) {
+    float4 x[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) x[r] = ld_peer_f4(stage[r] + v * 4);
+    float4 acc = x[0];
+#pragma unroll
+    for (int r = 1; r < NR; ++r) add4(acc, x[r]);
+    return acc;
+  }
+  // some ranks skipped (src/group.h:206-208: the side without gradients adopts the other's): sequential, rare
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool first = true;
+#pragma unroll 1
+  for (int r = 0; r < NR; ++r) {
+    if (!(mask & (1u << r))) continue;
+    const float4 x = ld_peer_f4(stage[r] + v * 4);
+    if (first) {
+      acc = x;
+      first = false;
+    } else {
+      add4(acc, x);
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float4 scale_vec(const float4& a, float s, bool do_scale) {
+  if (!do_scale) return a;
+  return make_float4(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s), __fmul_rn(a.w, s));
+}
+
+__device__ __forceinline__ void write_result(const ArParams& p, const mb_ar_hdr& tot) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.result->sum = tot;
+    p.result->status = MB_OK;
+    p.result->epoch = p.epoch;
+    __threadfence_system();
+  }
+}
+
+// ---- K-A2 one-shot ----------------------------------------------------------------------------------------------
+
+template <int NR>
+__global__ void __launch_bounds__(kArThreads, 2) ar_oneshot_kernel(const __grid_constant__ ArParams p) {
+  __shared__ uint32_t s_off[kArMaxTensors];
+  __shared__ mb_ar_hdr s_total;
+  __shared__ uint32_t s_mask;
+  load_offsets(s_off, p.dst_tab, p.ntensors);
+  publish_header(p);
+  if (!block_barrier(p, false)) {
+    report_failure(p);
+    return;
+  }
+  gather_headers(p, &s_total, &s_mask);
+  const uint32_t mask = s_mask;
+  const mb_ar_hdr tot = s_total;
+  const bool do_scale = p.scale && tot.num_gradients != 0;
+  const float s = reduce_scale(p, tot);
+  const uint64_t stride = (uint64_t)gridDim.x * kArThreads;
+  for (uint64_t v = (uint64_t)blockIdx.x * kArThreads + threadIdx.x; v < p.total_vec; v += stride) {
+    float4 r = reduce_vec<NR>(p.stage, mask, v);  // mask == 0 -> zeros (src/accumulator.cc:426-428)
+    r = scale_vec(r, s, do_scale);
+    scatter_vec(p.dst_tab, s_off, p.ntensors, v, r);
+  }
+  write_result(p, tot);
+}
+
+// ---- K-A2 two-shot ----------------------------------------------------------------------------------------------
+
+template <int NR>
+__global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_constant__ ArParams p) {
+  __shared__ uint32_t s_off[kArMaxTensors];
+  __shared__ mb_ar_hdr s_total;
+  __shared__ uint32_t s_mask;
+  load_offsets(s_off, p.dst_tab, p.ntensors);
+  publish_header(p);
+  if (!block_barrier(p, false)) {
+    report_failure(p);
+    return;
+  }
+  gather_headers(p, &s_total, &s_mask);
+  const uint32_t mask = s_mask;
+  const mb_ar_hdr tot = s_total;
+  const bool do_scale = p.scale && tot.num_gradients != 0;
+  const float s = reduce_scale(p, tot);
+  const uint64_t stride = (uint64_t)gridDim.x * kArThreads;
+  const uint64_t j0 = (uint64_t)blockIdx.x * kArThreads + threadIdx.x;
+  // phase 1: reduce my slice, write it to my destinations and into every peer's staging (in place: slice `rank` of a
+  // peer's staging is read only by me, and I overwrite an element only after I have loaded it)
+  {
+    const uint64_t base = (uint64_t)p.rank * p.slice_vec;
+    for (uint64_t j = j0; j < p.slice_vec; j += stride) {
+      const uint64_t v = base + j;
+      if (v >= p.total_vec) break;
+      float4 r = reduce_vec<NR>(p.stage, mask, v);
+      r = scale_vec(r, s, do_scale);
+#pragma unroll
+      for (int q = 0; q < NR; ++q)
+        if (q != p.rank) st_f4(p.stage[q] + v * 4, r);
+      scatter_vec(p.dst_tab, s_off, p.ntensors, v, r);
+    }
+  }
+  if (!block_barrier(p, true)) {
+    report_failure(p);
+    return;
+  }
+  // phase 2: the other slices are now complete in my own staging; block b reads exactly what the peers' block b wrote
+  float* mine = p.stage[p.rank];
+#pragma unroll 1
+  for (int q = 0; q < NR; ++q) {
+    if (q == p.rank) continue;
+    const uint64_t base = (uint64_t)q * p.slice_vec;
+    for (uint64_t j = j0; j < p.slice_vec; j += stride) {
+      const uint64_t v = base + j;
+      if (v >= p.total_vec) break;
+      const float4 r = ld_peer_f4(mine + v * 4);
+      scatter_vec(p.dst_tab, s_off, p.ntensors, v, r);
+    }
+  }
+  write_result(p, tot);
+}
+
+using ArKernel = void (*)(const ArParams);
+
+template <int NR>
+ArKernel pick(bool twoshot) {
+  return twoshot ? (ArKernel)ar_twoshot_kernel<NR> : (ArKernel)ar_oneshot_kernel<NR>;
+}
+
+ArKernel kernel_for(int world, bool twoshot) {
+  switch (world) {
+    case 1: return pick<1>(twoshot);
+    case 2: return pick<2>(twoshot);
+    case 3: return pick<3>(twoshot);
+    case 4: return pick<4>(twoshot);
+    case 5: return pick<5>(twoshot);
+    case 6: return pick<6>(twoshot);
+    case 7: return pick<7>(twoshot);
+    case 8: return pick<8>(twoshot);
+  }
+  return nullptr;
+}
+
+// ---- host helpers ------------------------------------------------------------------------------------------------
+
+uint64_t flat_layout(const uint64_t* numel, int n, std::vector<TensorEnt>* out, const void* const* ptrs) {
+  uint64_t off = 0;
+  if (out) out->resize(n);
+  for (int i = 0; i < n; ++i) {
+    if (out) (*out)[i] = TensorEnt{reinterpret_cast<uint64_t>(ptrs ? ptrs[i] : nullptr), off, numel[i]};
+    off += (numel[i] + 3) & ~3ull;
+  }
+  return off;
+}
+
+// Upload a tensor table if it differs from what the device already holds.
+int sync_table(mb_ar_ctx* ctx, int which, const std::vector<TensorEnt>& tab, cudaStream_t stream) {
+  auto& cache = ctx->tab_host[which];
+  if (cache.size() == tab.size() &&
+      (tab.empty() || std::memcmp(cache.data(), tab.data(), tab.size() * sizeof(TensorEnt)) == 0))
+    return MB_OK;
+  cache = tab;
+  if (!tab.empty()) {
+    // pageable source: the runtime stages it before returning, and the copy is ordered on `stream` after any kernel
+    // still reading the previous table
+    MB_CUDA(cudaMemcpyAsync(ctx->tab_dev[which], cache.data(), tab.size() * sizeof(TensorEnt),
+                            cudaMemcpyHostToDevice, stream));
+  }
+  return MB_OK;
+}
+
+float* slot_buffer(mb_ar_ctx* ctx, float* base, int slot) {
+  const uint64_t floats = ctx->max_bytes / 4;
+  return base + ((uint64_t)slot * 2 + (uint64_t)ctx->parity[slot]) * floats;
+}
+
+uint64_t env_u64(const char* name, uint64_t dflt) {
+  const char* e = std::getenv(name);
+  if (!e || !*e) return dflt;
+  return std::strtoull(e, nullptr, 0);
+}
+
+uint64_t twoshot_min_bytes(int world) {
+  // below this the single barrier of the one-shot kernel wins; above it the (N-1)x ingress dominates.
+  // MB_AR_TWOSHOT_MIN_BYTES overrides (measured crossovers are recorded in DESIGN.md).
+  static const uint64_t forced = env_u64("MB_AR_TWOSHOT_MIN_BYTES", 0);
+  if (forced) return forced;
+  if (world <= 2) return ~0ull;  // two-shot moves the same bytes as one-shot at N=2
+  if (world <= 4) return 1ull << 20;
+  return 256ull << 10;
+}
+
+}  // namespace
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+uint64_t mb_ar_flat_numel(const uint64_t* numel, int ntensors) {
+  if (!numel || ntensors <= 0) return 0;
+  return flat_layout(numel, ntensors, nullptr, nullptr);
+}
+
+int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int nslots, mb_ar_ctx** out) {
+  MB_CHECK_ARG(out != nullptr, "mb_ar_ctx_create: out is null");
+  *out = nullptr;
+  MB_CHECK_ARG(world >= 1 && world <= MB_AR_MAX_WORLD, "mb_ar_ctx_create: world %d not in [1,%d]", world,
+               MB_AR_MAX_WORLD);
+  MB_CHECK_ARG(rank >= 0 && rank < world, "mb_ar_ctx_create: rank %d not in [0,%d)", rank, world);
+  MB_CHECK_ARG(nslots >= 1 && nslots <= MB_AR_MAX_SLOTS, "mb_ar_ctx_create: nslots %d not in [1,%d]", nslots,
+               MB_AR_MAX_SLOTS);
+  MB_CHECK_ARG(max_bytes > 0, "mb_ar_ctx_create: max_bytes is 0");
+  DeviceGuard g(device);
+  if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+  mb_ar_ctx* ctx = new (std::nothrow) mb_ar_ctx();
+  if (!ctx) return MB_ENOMEM;
+  ctx->rank = rank;
+  ctx->world = world;
+  ctx->device = device;
+  ctx->nslots = nslots;
+  ctx->max_bytes = (max_bytes + 15) & ~15ull;
+  auto fail = [&](int rc) {
+    mb_ar_ctx_destroy(ctx);
+    return rc;
+  };
+#define MB_TRY(expr)                                                                  \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess) return fail(cuda_fail(e__, #expr, __FILE__, __LINE__));   \
+  } while (0)
+  const uint64_t staging_bytes = ctx->max_bytes * 2 * (uint64_t)nslots;
+  MB_TRY(cudaMalloc(&ctx->staging, staging_bytes));
+  MB_TRY(cudaMemset(ctx->staging, 0, staging_bytes));
+  MB_TRY(cudaMalloc(&ctx->sync, sizeof(SyncBlock)));
+  MB_TRY(cudaMemset(ctx->sync, 0, sizeof(SyncBlock)));
+  MB_TRY(cudaHostAlloc(&ctx->result_host, sizeof(HostResult) * MB_AR_MAX_SLOTS, cudaHostAllocMapped));
+  std::memset(ctx->result_host, 0, sizeof(HostResult) * MB_AR_MAX_SLOTS);
+  MB_TRY(cudaHostGetDevicePointer(&ctx->result_dev, ctx->result_host, 0));
+  MB_TRY(cudaHostAlloc(&ctx->abort_host, sizeof(uint32_t), cudaHostAllocMapped));
+  *ctx->abort_host = 0;
+  MB_TRY(cudaHostGetDevicePointer(&ctx->abort_dev, ctx->abort_host, 0));
+  for (int w = 0; w < 2; ++w) MB_TRY(cudaMalloc(&ctx->tab_dev[w], sizeof(TensorEnt) * kArMaxTensors));
+  MB_TRY(cudaDeviceSynchronize());
+#undef MB_TRY
+  ctx->peer_staging[rank] = ctx->staging;
+  ctx->peer_sync[rank] = ctx->sync;
+  ctx->imported[rank] = true;
+  *out = ctx;
+  return MB_OK;
+}
+
+static void close_peers(mb_ar_ctx* ctx) {
+  for (int r = 0; r < MB_AR_MAX_WORLD; ++r) {
+    if (ctx->ipc_opened[r]) {
+      if (ctx->peer_staging[r]) cudaIpcCloseMemHandle(ctx->peer_staging[r]);
+      if (ctx->peer_sync[r]) cudaIpcCloseMemHandle(ctx->peer_sync[r]);
+    }
+    ctx->ipc_opened[r] = false;
+    ctx->imported[r] = false;
+    ctx->peer_staging[r] = nullptr;
+    ctx->peer_sync[r] = nullptr;
+  }
+}
+
+int mb_ar_ctx_destroy(mb_ar_ctx* ctx) {
+  if (!ctx) return MB_OK;
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->imported[ctx->rank] = false;
+  ctx->peer_staging[ctx->rank] = nullptr;
+  ctx->peer_sync[ctx->rank] = nullptr;
+  close_peers(ctx);
+  if (ctx->staging) cudaFree(ctx->staging);
+  if (ctx->sync) cudaFree(ctx->sync);
+  if (ctx->result_host) cudaFreeHost(ctx->result_host);
+  if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
+  for (int w = 0; w < 2; ++w)
+    if (ctx->tab_dev[w]) cudaFree(ctx->tab_dev[w]);
+  delete ctx;
+  return MB_OK;
+}
+
+int mb_ar_ctx_export(mb_ar_ctx* ctx, mb_ar_handle* out) {
+  MB_CHECK_ARG(ctx && out, "mb_ar_ctx_export: null argument");
+  DeviceGuard g(ctx->device);
+  std::memset(out, 0, sizeof(*out));
+  HandleImpl h;
+  std::memset(&h, 0, sizeof(h));
+  h.magic = kHandleMagic;
+  h.pid = (int32_t)getpid();
+  h.device = ctx->device;
+  h.rank = ctx->rank;
+  h.staging_ptr = reinterpret_cast<uint64_t>(ctx->staging);
+  h.sync_ptr = reinterpret_cast<uint64_t>(ctx->sync);
+  h.max_bytes = ctx->max_bytes;
+  h.nslots = ctx->nslots;
+  h.ipc_ok = 1;
+  if (cudaIpcGetMemHandle(&h.h_staging, ctx->staging) != cudaSuccess ||
+      cudaIpcGetMemHandle(&h.h_sync, ctx->sync) != cudaSuccess) {
+    cudaGetLastError();  // same-process peers can still import by pointer
+    h.ipc_ok = 0;
+  }
+  std::memcpy(out->bytes, &h, sizeof(h));
+  return MB_OK;
+}
+
+int mb_ar_ctx_import(mb_ar_ctx* ctx, int peer_rank, const mb_ar_handle* handle) {
+  MB_CHECK_ARG(ctx && handle, "mb_ar_ctx_import: null argument");
+  MB_CHECK_ARG(peer_rank >= 0 && peer_rank < ctx->world, "mb_ar_ctx_import: peer rank %d not in [0,%d)", peer_rank,
+               ctx->world);
+  HandleImpl h;
+  std::memcpy(&h, handle->bytes, sizeof(h));
+  MB_CHECK_ARG(h.magic == kHandleMagic, "mb_ar_ctx_import: not an mb_ar_handle");
+  MB_CHECK_ARG(h.max_bytes == ctx->max_bytes && h.nslots == ctx->nslots,
+               "mb_ar_ctx_import: peer %d was created with max_bytes=%llu nslots=%d, local ctx has %llu/%d", peer_rank,
+               (unsigned long long)h.max_bytes, h.nslots, (unsigned long long)ctx->max_bytes, ctx->nslots);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  if (peer_rank == ctx->rank) return MB_OK;
+  DeviceGuard g(ctx->device);
+  if (ctx->imported[peer_rank]) {
+    if (ctx->ipc_opened[peer_rank]) {
+      cudaIpcCloseMemHandle(ctx->peer_staging[peer_rank]);
+      cudaIpcCloseMemHandle(ctx->peer_sync[peer_rank]);
+    }
+    ctx->imported[peer_rank] = ctx->ipc_opened[peer_rank] = false;
+  }
+  if (h.pid == (int32_t)getpid()) {
+    if (h.device != ctx->device) {
+      int can = 0;
+      MB_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
+      if (!can) {
+        set_error("mb_ar_ctx_import: device %d cannot access peer device %d", ctx->device, h.device);
+        return MB_ESTATE;
+      }
+      cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+    }
+    ctx->peer_staging[peer_rank] = reinterpret_cast<float*>(h.staging_ptr);
+    ctx->peer_sync[peer_rank] = reinterpret_cast<SyncBlock*>(h.sync_ptr);
+    ctx->ipc_opened[peer_rank] = false;
+  } else {
+    if (!h.ipc_ok) {
+      set_error("mb_ar_ctx_import: peer %d could not export CUDA IPC handles", peer_rank);
+      return MB_ESTATE;
+    }
+    void* ps = nullptr;
+    void* py = nullptr;
+    MB_CUDA(cudaIpcOpenMemHandle(&ps, h.h_staging, cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaIpcOpenMemHandle(&py, h.h_sync, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaIpcCloseMemHandle(ps);
+      return cuda_fail(e, "cudaIpcOpenMemHandle(sync)", __FILE__, __LINE__);
+    }
+    ctx->peer_staging[peer_rank] = static_cast<float*>(ps);
+    ctx->peer_sync[peer_rank] = static_cast<SyncBlock*>(py);
+    ctx->ipc_opened[peer_rank] = true;
+  }
+  ctx->imported[peer_rank] = true;
+  return MB_OK;
+}
+
+int mb_ar_ctx_reset(mb_ar_ctx* ctx, int new_rank, int new_world) {
+  MB_CHECK_ARG(ctx != nullptr, "mb_ar_ctx_reset: null ctx");
+  MB_CHECK_ARG(new_world >= 1 && new_world <= MB_AR_MAX_WORLD && new_rank >= 0 && new_rank < new_world,
+               "mb_ar_ctx_reset: bad rank/world %d/%d", new_rank, new_world);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  DeviceGuard g(ctx->device);
+  *ctx->abort_host = 1;  // release any kernel still spinning on a dead peer
+  MB_CUDA(cudaDeviceSynchronize());
+  ctx->imported[ctx->rank] = false;
+  ctx->peer_staging[ctx->rank] = nullptr;
+  ctx->peer_sync[ctx->rank] = nullptr;
+  close_peers(ctx);
+  MB_CUDA(cudaMemset(ctx->sync, 0, sizeof(SyncBlock)));
+  MB_CUDA(cudaDeviceSynchronize());
+  *ctx->abort_host = 0;
+  ctx->epoch = 0;
+  for (int s = 0; s < MB_AR_MAX_SLOTS; ++s) ctx->parity[s] = 0;
+  ctx->rank = new_rank;
+  ctx->world = new_world;
+  ctx->peer_staging[new_rank] = ctx->staging;
+  ctx->peer_sync[new_rank] = ctx->sync;
+  ctx->imported[new_rank] = true;
+  return MB_OK;
+}
+
+void* mb_ar_staging(mb_ar_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= ctx->nslots) return nullptr;
+  return slot_buffer(ctx, ctx->staging, slot);
+}
+
+int mb_ar_world(mb_ar_ctx* ctx) { return ctx ? ctx->world : MB_EINVAL; }
+int mb_ar_rank(mb_ar_ctx* ctx) { return ctx ? ctx->rank : MB_EINVAL; }
+
+int mb_ar_abort(mb_ar_ctx* ctx) {
+  MB_CHECK_ARG(ctx != nullptr, "mb_ar_abort: null ctx");
+  *reinterpret_cast<volatile uint32_t*>(ctx->abort_host) = 1;
+  return MB_OK;
+}
+
+int mb_ar_stage(mb_ar_ctx* ctx, int slot, const float* const* grads, const uint64_t* numel, int ntensors,
+                int accumulate, int zero_src, mb_stream_t stream_) {
+  MB_CHECK_ARG(ctx && grads && numel, "mb_ar_stage: null argument");
+  MB_CHECK_ARG(slot >= 0 && slot < ctx->nslots, "mb_ar_stage: slot %d out of range", slot);
+  MB_CHECK_ARG(ntensors >= 1 && ntensors <= kArMaxTensors, "mb_ar_stage: ntensors %d not in [1,%d]", ntensors,
+               kArMaxTensors);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  std::vector<TensorEnt> tab;
+  const uint64_t total = flat_layout(numel, ntensors, &tab, reinterpret_cast<const void* const*>(grads));
+  MB_CHECK_ARG(total * 4 <= ctx->max_bytes, "mb_ar_stage: %llu bytes exceed the context's max_bytes %llu",
+               (unsigned long long)(total * 4), (unsigned long long)ctx->max_bytes);
+  if (total == 0) return 0;
+  int rc = sync_table(ctx, 0, tab, stream);
+  if (rc) return rc;
+  StageParams p;
+  p.staging = slot_buffer(ctx, ctx->staging, slot);
+  p.tab = ctx->tab_dev[0];
+  p.ntensors = (uint32_t)ntensors;
+  p.accumulate = accumulate;
+  p.zero_src = zero_src;
+  p.total_vec = total / 4;
+  const int sms = sm_count(ctx->device);
+  if (sms <= 0) return MB_ECUDA;
+  const uint64_t want = (p.total_vec + kArThreads - 1) / kArThreads;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 4);
+  ar_stage_kernel<<<grid, kArThreads, 0, stream>>>(p);
+  MB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int mb_ar_allreduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* const* dst, const uint64_t* numel,
+                    int ntensors, float* flat_dst, uint64_t flat_numel, int scale_by_num_gradients, int algo,
+                    uint32_t timeout_ms, mb_stream_t stream_) {
+  MB_CHECK_ARG(ctx && my_hdr, "mb_ar_allreduce: null argument");
+  MB_CHECK_ARG(slot >= 0 && slot < ctx->nslots, "mb_ar_allreduce: slot %d out of range", slot);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  std::vector<TensorEnt> tab;
+  uint64_t total;
+  if (dst) {
+    MB_CHECK_ARG(numel != nullptr, "mb_ar_allreduce: numel is null");
+    MB_CHECK_ARG(ntensors >= 1 && ntensors <= kArMaxTensors, "mb_ar_allreduce: ntensors %d not in [1,%d]", ntensors,
+                 kArMaxTensors);
+    total = flat_layout(numel, ntensors, &tab, reinterpret_cast<const void* const*>(dst));
+  } else {
+    MB_CHECK_ARG(flat_dst != nullptr, "mb_ar_allreduce: neither dst nor flat_dst given");
+    const void* ptr = flat_dst;
+    total = flat_layout(&flat_numel, 1, &tab, &ptr);
+    ntensors = 1;
+  }
+  MB_CHECK_ARG(total * 4 <= ctx->max_bytes, "mb_ar_allreduce: %llu bytes exceed the context's max_bytes %llu",
+               (unsigned long long)(total * 4), (unsigned long long)ctx->max_bytes);
+  MB_CHECK_ARG(total < (1ull << 33), "mb_ar_allreduce: tensor list too large");
+  for (int r = 0; r < ctx->world; ++r) {
+    if (!ctx->imported[r]) {
+      set_error("mb_ar_allreduce: peer %d has not been imported", r);
+      return MB_ESTATE;
+    }
+  }
+  int rc = sync_table(ctx, 1, tab, stream);
+  if (rc) return rc;
+
+  ArParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int r = 0; r < ctx->world; ++r) {
+    p.stage[r] = slot_buffer(ctx, ctx->peer_staging[r], slot);
+    p.sync[r] = ctx->peer_sync[r];
+  }
+  p.dst_tab = ctx->tab_dev[1];
+  p.ntensors = (uint32_t)ntensors;
+  p.epoch = ++ctx->epoch;
+  p.total_vec = total / 4;
+  p.slice_vec = (p.total_vec + ctx->world - 1) / ctx->world;
+  p.my_hdr = *my_hdr;
+  p.my_hdr.has_grads = my_hdr->has_grads ? 1 : 0;
+  p.rank = ctx->rank;
+  p.world = ctx->world;
+  p.scale = scale_by_num_gradients ? 1 : 0;
+  p.result = ctx->result_dev + slot;
+  p.abort_flag = ctx->abort_dev;
+  p.timeout_ns = (uint64_t)(timeout_ms ? timeout_ms : 30000u) * 1000000ull;
+  ctx->parity[slot] ^= 1;  // the next round on this slot stages into the other buffer (see header comment)
+
+  bool twoshot = false;
+  if (ctx->world > 1) {
+    if (algo == MB_AR_ALGO_TWOSHOT) twoshot = true;
+    else if (algo == MB_AR_ALGO_AUTO) twoshot = total * 4 >= twoshot_min_bytes(ctx->world);
+  }
+  const int sms = sm_count(ctx->device);
+  if (sms <= 0) return MB_ECUDA;
+  const uint64_t work_vec = twoshot ? p.slice_vec : p.total_vec;
+  uint64_t want = (work_vec + kArThreads - 1) / kArThreads;
+  if (want == 0) want = 1;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)sms * 2, kArMaxBlocks));
+  ArKernel k = kernel_for(ctx->world, twoshot);
+  k<<<grid, kArThreads, 0, stream>>>(p);
+  MB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int mb_ar_result(mb_ar_ctx* ctx, int slot, mb_ar_hdr* sum_out, int* status_out) {
+  MB_CHECK_ARG(ctx != nullptr, "mb_ar_result: null ctx");
+  MB_CHECK_ARG(slot >= 0 && slot < ctx->nslots, "mb_ar_result: slot %d out of range", slot);
+  const volatile HostResult* r = ctx->result_host + slot;
+  if (sum_out) {
+    sum_out->num_gradients = r->sum.num_gradients;
+    sum_out->num_skipped = r->sum.num_skipped;
+    sum_out->batch_size = r->sum.batch_size;
+    sum_out->has_grads = r->sum.has_grads;
+  }
+  if (status_out) *status_out = r->status;
+  return MB_OK;
+}
+
+}  // extern "C"
