@@ -1,6 +1,6 @@
 /*
  * moolib_b200.h -- the thin C-ABI between the C++/pybind11 host layer (moolib_b200/csrc/host, which mirrors
- * moolib's Python API) and the hand-written sm_100a kernels (moolib_b200/csrc/*.cu -> libmoolib_b200.so).
+ * moolib's Python API) and the hand-written sm_100a kernels (the .cu files under moolib_b200/csrc -> libmoolib_b200.so).
  *
  * Nothing here exists in the reference: the reference has no device code at all (SURVEY.md correction 3).  Each
  * entry point names the reference code whose arithmetic/byte movement it replaces ("replaces: file:line", paths

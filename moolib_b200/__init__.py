@@ -1,0 +1,30 @@
+"""moolib_b200: the two data-parallel hot paths of moolib (gradient allreduce, observation batch gather) as
+hand-written sm_100a kernels behind moolib's own Python API.
+
+The names below are the ones `py/moolib/__init__.py` of the reference re-exports for these paths; they come from the
+compiled host layer `moolib_b200._C` (C++/pybind11 over torch tensors) which calls the kernels through the C-ABI in
+include/moolib_b200.h.  There is no Python or CPU fallback: importing fails loudly if the native pieces are missing.
+"""
+import os as _os
+
+_here = _os.path.dirname(_os.path.abspath(__file__))
+if not _os.path.exists(_os.path.join(_here, "lib", "libmoolib_b200.so")):
+    raise ImportError("moolib_b200/lib/libmoolib_b200.so is missing; build it with `python -m moolib_b200.build`")
+
+import torch as _torch  # noqa: E402,F401  (libtorch must be loaded before the extension)
+
+try:
+    from . import _C  # noqa: E402
+except ImportError as e:  # pragma: no cover
+    raise ImportError(
+        "moolib_b200._C (the compiled host layer) is missing or failed to load; build it with "
+        "`python -m moolib_b200.build`") from e
+
+from ._C import Batcher  # noqa: E402,F401
+
+for _name in ("Accumulator", "Group", "Rpc", "Broker", "EnvPool", "EnvStepper", "EnvStepperFuture", "Future",
+              "AllReduce", "create_uid", "set_log_level", "set_logging", "set_max_threads"):
+    if hasattr(_C, _name):
+        globals()[_name] = getattr(_C, _name)
+
+__version__ = "0.1.0"

@@ -1,0 +1,48 @@
+// Host layer (C++/pybind11 over torch tensors) of moolib_b200: mirrors the Python API of the reference's `moolib._C`
+// for the two hot paths and calls the sm_100a kernels through the C-ABI in include/moolib_b200.h.
+// torch here is the owner of device memory, streams and dtypes -- plumbing, not the product.
+#pragma once
+
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "moolib_b200.h"
+
+namespace py = pybind11;
+
+namespace mbh {
+
+// Throws std::runtime_error (-> Python RuntimeError, as the reference does for its own errors) on a negative code.
+inline int check(int rc, const char* what) {
+  if (rc < 0) {
+    throw std::runtime_error(std::string(what) + ": moolib_b200 error " + std::to_string(rc) + ": " + mb_last_error());
+  }
+  return rc;
+}
+
+inline mb_stream_t current_stream(int device) {
+  return static_cast<mb_stream_t>(c10::cuda::getCurrentCUDAStream(device).stream());
+}
+
+// torch.Tensor <-> Python (src/tensorpython.cc:18-30 in the reference)
+inline bool is_tensor(const py::handle& h) { return THPVariable_Check(h.ptr()); }
+inline torch::Tensor to_tensor(const py::handle& h) { return THPVariable_Unpack(h.ptr()); }
+inline py::object to_python(const torch::Tensor& t) { return py::reinterpret_steal<py::object>(THPVariable_Wrap(t)); }
+
+// Number of kernels this process launched through the host layer (bench.py's gpu_launches claim).
+uint64_t& launch_counter();
+
+void bind_batcher(py::module_& m);
+void bind_accumulator(py::module_& m);
+void bind_envpool(py::module_& m);
+void bind_rpc(py::module_& m);
+
+}  // namespace mbh

@@ -299,35 +299,49 @@ __device__ __forceinline__ void add4(float4& a, const float4& b) {
   a.w = __fadd_rn(a.w, b.w);
 }
 
-// Sum of element v over the ranks in `mask`, ascending rank order, fp32.  Fast path (every rank contributes): all NR
-// loads are issued before the first add so NR x 16 B are in flight per thread.
-template <int NR>
-__device__ __forceinline__ float4 reduce_vec(float* const* stage, uint32_t mask, uint64_t v) {
+// Sum of element v over the ranks in `mask`, ascending rank order, fp32, for U vectors at once (v[k], k < U).  Fast
+// path (every rank contributes): all U*NR loads are issued before the first add, so U*NR*16 B are in flight per thread
+// -- NVLink latency is ~2 us, bandwidth needs megabytes in flight (B300_MICROARCH "NVLink").
+template <int NR, int U>
+__device__ __forceinline__ void reduce_vecs(float* const* stage, uint32_t mask, const uint64_t (&v)[U],
+                                            float4 (&acc)[U]) {
   if (mask == (1u << NR) - 1u) {
-    float4 x[NR];
+    float4 x[U][NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) x[r] = ld_peer_f4(stage[r] + v * 4);
-    float4 acc = x[0];
+    for (int k = 0; k < U; ++k)
 #pragma unroll
-    for (int r = 1; r < NR; ++r) add4(acc, x[r]);
-    return acc;
+      for (int r = 0; r < NR; ++r) x[k][r] = ld_peer_f4(stage[r] + v[k] * 4);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      acc[k] = x[k][0];
+#pragma unroll
+      for (int r = 1; r < NR; ++r) add4(acc[k], x[k][r]);
+    }
+    return;
   }
   // some ranks skipped (src/group.h:206-208: the side without gradients adopts the other's): sequential, rare
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  bool first = true;
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool first = true;
 #pragma unroll 1
-  for (int r = 0; r < NR; ++r) {
-    if (!(mask & (1u << r))) continue;
-    const float4 x = ld_peer_f4(stage[r] + v * 4);
-    if (first) {
-      acc = x;
-      first = false;
-    } else {
-      add4(acc, x);
+    for (int r = 0; r < NR; ++r) {
+      if (!(mask & (1u << r))) continue;
+      const float4 x = ld_peer_f4(stage[r] + v[k] * 4);
+      if (first) {
+        acc[k] = x;
+        first = false;
+      } else {
+        add4(acc[k], x);
+      }
     }
   }
-  return acc;
 }
+
+template <int NR>
+struct Unroll {
+  static constexpr int value = NR >= 8 ? 1 : NR >= 4 ? 2 : 4;
+};
 
 __device__ __forceinline__ float4 scale_vec(const float4& a, float s, bool do_scale) {
   if (!do_scale) return a;
@@ -361,11 +375,19 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_oneshot_kernel(const __grid_
   const mb_ar_hdr tot = s_total;
   const bool do_scale = p.scale && tot.num_gradients != 0;
   const float s = reduce_scale(p, tot);
+  constexpr int U = Unroll<NR>::value;
   const uint64_t stride = (uint64_t)gridDim.x * kArThreads;
-  for (uint64_t v = (uint64_t)blockIdx.x * kArThreads + threadIdx.x; v < p.total_vec; v += stride) {
-    float4 r = reduce_vec<NR>(p.stage, mask, v);  // mask == 0 -> zeros (src/accumulator.cc:426-428)
-    r = scale_vec(r, s, do_scale);
-    scatter_vec(p.dst_tab, s_off, p.ntensors, v, r);
+  for (uint64_t v0 = (uint64_t)blockIdx.x * kArThreads + threadIdx.x; v0 < p.total_vec; v0 += stride * U) {
+    uint64_t v[U];
+    float4 r[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) v[k] = min(v0 + (uint64_t)k * stride, p.total_vec - 1);  // clamped, stores predicated
+    reduce_vecs<NR, U>(p.stage, mask, v, r);  // mask == 0 -> zeros (src/accumulator.cc:426-428)
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (v0 + (uint64_t)k * stride < p.total_vec)
+        scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], scale_vec(r[k], s, do_scale));
+    }
   }
   write_result(p, tot);
 }
@@ -393,16 +415,24 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_
   // phase 1: reduce my slice, write it to my destinations and into every peer's staging (in place: slice `rank` of a
   // peer's staging is read only by me, and I overwrite an element only after I have loaded it)
   {
+    constexpr int U = Unroll<NR>::value;
     const uint64_t base = (uint64_t)p.rank * p.slice_vec;
-    for (uint64_t j = j0; j < p.slice_vec; j += stride) {
-      const uint64_t v = base + j;
-      if (v >= p.total_vec) break;
-      float4 r = reduce_vec<NR>(p.stage, mask, v);
-      r = scale_vec(r, s, do_scale);
+    const uint64_t end = min(p.total_vec, base + p.slice_vec);  // my slice is [base, end)
+    for (uint64_t v0 = base + j0; v0 < end; v0 += stride * U) {
+      uint64_t v[U];
+      float4 r[U];
 #pragma unroll
-      for (int q = 0; q < NR; ++q)
-        if (q != p.rank) st_f4(p.stage[q] + v * 4, r);
-      scatter_vec(p.dst_tab, s_off, p.ntensors, v, r);
+      for (int k = 0; k < U; ++k) v[k] = min(v0 + (uint64_t)k * stride, end - 1);
+      reduce_vecs<NR, U>(p.stage, mask, v, r);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (v0 + (uint64_t)k * stride >= end) continue;
+        const float4 o = scale_vec(r[k], s, do_scale);
+#pragma unroll
+        for (int q = 0; q < NR; ++q)
+          if (q != p.rank) st_f4(p.stage[q] + v[k] * 4, o);
+        scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], o);
+      }
     }
   }
   if (!block_barrier(p, true)) {

@@ -5,9 +5,11 @@
 //   * copy2d_ldg_kernel : 256-thread CTAs, persistent grid-stride over 16 KiB tiles, 4x16 B loads in flight per
 //                         thread (ld.global.nc.L1::no_allocate.v4), coalesced 128 B-per-4-lanes stores.  Handles
 //                         every alignment (head / 16 B body / tail, or 8/4/1 B lanes when src and dst are skewed).
-//   * copy2d_tma_kernel : one elected lane per warp drives a ring of cp.async.bulk (UBLKCP) global->shared loads
-//                         completing on mbarriers and cp.async.bulk shared->global stores; no register staging.
-//                         Needs 16 B aligned src/dst/pitch/row_bytes; used when the whole table qualifies.
+//   * copy2d_hybrid_kernel : for tables that carry bulk data.  Warps 0..W-1: one elected lane per warp drives a ring
+//                         of cp.async.bulk (UBLKCP) global->shared loads completing on mbarriers and cp.async.bulk
+//                         shared->global stores -- no register staging -- over the jobs that are 16 B aligned in
+//                         src/dst/pitch/row_bytes.  The remaining warps run the LDG path over the table's other
+//                         jobs (tiny leaves such as reward/done, skewed rows) in the SAME launch.
 // Both are HBM-bound (2 x payload bytes); neither touches tensor cores.
 #include "mb_common.cuh"
 
@@ -24,9 +26,10 @@ constexpr uint32_t kTileBytes = 16384;  // = kCopyThreads * 4 * 16 B: one unroll
 constexpr int kMaxJobs = MB_COPY_MAX_INLINE_JOBS;
 
 enum : uint8_t {
-  kModeBigRows = 0,     // row_bytes >= kTileBytes: a tile is a contiguous span inside one row
-  kModeSmallVec16 = 1,  // small rows, everything 16 B aligned: a tile is `rpt` whole rows, flat 16 B vector loop
-  kModeSmallGeneric = 2 // small rows, arbitrary alignment: a tile is `rpt` rows, one warp per row
+  kModeBigRows = 0,      // row_bytes >= kTileBytes: a tile is a contiguous span inside one row
+  kModeSmallVec16 = 1,   // small rows, everything 16 B aligned: a tile is `rpt` whole rows, flat 16 B vector loop
+  kModeSmallGeneric = 2, // small rows, arbitrary alignment: a tile is `rpt` rows, one warp per row
+  kModeTma = 3           // bulk-async class: a tile is <= tma_tile bytes inside one row (jobs [0, n_tma))
 };
 
 struct CopyParams {
@@ -35,7 +38,11 @@ struct CopyParams {
   uint32_t aux[kMaxJobs];             // big rows: tiles per row; small rows: rows per tile
   uint8_t mode[kMaxJobs];
   uint32_t njobs;
-  uint32_t pad_;
+  uint32_t n_tma;      // jobs [0, n_tma) are the bulk-async class (hybrid kernel only)
+  uint32_t tma_tile;   // bytes per bulk copy
+  uint16_t tma_warps;  // warps driving rings
+  uint8_t tma_stages;
+  uint8_t tma_stores;  // store groups allowed to be still reading shared memory
 };
 static_assert(sizeof(CopyParams) <= 4000, "CopyParams must fit the 4 KiB kernel parameter block");
 
@@ -152,16 +159,16 @@ __device__ __forceinline__ void copy_span(const uint8_t* __restrict__ src, uint8
   }
 }
 
-// One tile of one job, executed by the whole CTA.
-__device__ __forceinline__ void run_tile(const mb_copy_job& j, uint32_t mode, uint32_t aux, uint32_t t) {
+// One tile of one job, executed by `nthr` cooperating threads (a whole CTA, or the LDG warps of a hybrid CTA).
+__device__ __forceinline__ void run_tile(const mb_copy_job& j, uint32_t mode, uint32_t aux, uint32_t t, uint32_t tid,
+                                         uint32_t nthr) {
   const uint8_t* src = static_cast<const uint8_t*>(j.src);
   uint8_t* dst = static_cast<uint8_t*>(j.dst);
   if (mode == kModeBigRows) {
     const uint32_t row = t / aux;
     const uint64_t col = (uint64_t)(t - row * aux) * kTileBytes;
     const uint64_t len = min((uint64_t)kTileBytes, j.row_bytes - col);
-    copy_span(src + (int64_t)row * j.src_pitch + col, dst + (int64_t)row * j.dst_pitch + col, len, threadIdx.x,
-              kCopyThreads);
+    copy_span(src + (int64_t)row * j.src_pitch + col, dst + (int64_t)row * j.dst_pitch + col, len, tid, nthr);
   } else {
     const uint64_t row0 = (uint64_t)t * aux;
     const uint32_t nrows = (uint32_t)min((uint64_t)aux, j.rows - row0);
@@ -170,22 +177,24 @@ __device__ __forceinline__ void run_tile(const mb_copy_job& j, uint32_t mode, ui
       const uint32_t total = nrows * vpr;  // <= kTileBytes/16
       const uint8_t* s0 = src + (int64_t)row0 * j.src_pitch;
       uint8_t* d0 = dst + (int64_t)row0 * j.dst_pitch;
-      uint4 v[4];
-      uint32_t r[4], c[4];
+      for (uint32_t base = 0; base < total; base += 4 * nthr) {
+        uint4 v[4];
+        uint32_t r[4], c[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t i = min(threadIdx.x + k * kCopyThreads, total - 1);  // clamped: see copy_vec16
-        r[k] = i / vpr;
-        c[k] = i - r[k] * vpr;
-        v[k] = ld_stream_v4(s0 + (int64_t)r[k] * j.src_pitch + (uint64_t)c[k] * 16);
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t i = min(base + tid + k * nthr, total - 1);  // clamped: see copy_vec16
+          r[k] = i / vpr;
+          c[k] = i - r[k] * vpr;
+          v[k] = ld_stream_v4(s0 + (int64_t)r[k] * j.src_pitch + (uint64_t)c[k] * 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (base + tid + k * nthr < total)
+            st_stream_v4(d0 + (int64_t)r[k] * j.dst_pitch + (uint64_t)c[k] * 16, v[k]);
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (threadIdx.x + k * kCopyThreads < total)
-          st_stream_v4(d0 + (int64_t)r[k] * j.dst_pitch + (uint64_t)c[k] * 16, v[k]);
     } else {
-      const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      for (uint32_t r = warp; r < nrows; r += kCopyThreads / 32) {
+      const uint32_t warp = tid >> 5, lane = tid & 31;
+      for (uint32_t r = warp; r < nrows; r += nthr / 32) {
         copy_span(src + (int64_t)(row0 + r) * j.src_pitch, dst + (int64_t)(row0 + r) * j.dst_pitch, j.row_bytes, lane,
                   32);
       }
@@ -193,16 +202,21 @@ __device__ __forceinline__ void run_tile(const mb_copy_job& j, uint32_t mode, ui
   }
 }
 
+__device__ __forceinline__ uint32_t find_job(const CopyParams& p, uint32_t t) {
+  // binary search: last job whose tile_start <= t (njobs <= 64 -> <= 6 steps, warp-uniform)
+  uint32_t lo = 0, hi = p.njobs;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (p.tile_start[mid] <= t) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_kernel(const __grid_constant__ CopyParams p) {
   const uint32_t total = p.tile_start[p.njobs];
   for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
-    // binary search: last job whose tile_start <= t (njobs <= 64 -> <= 6 steps, warp-uniform)
-    uint32_t lo = 0, hi = p.njobs;
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (p.tile_start[mid] <= t) lo = mid; else hi = mid;
-    }
-    run_tile(p.jobs[lo], p.mode[lo], p.aux[lo], t - p.tile_start[lo]);
+    const uint32_t j = find_job(p, t);
+    run_tile(p.jobs[j], p.mode[j], p.aux[j], t - p.tile_start[j], threadIdx.x, kCopyThreads);
   }
 }
 
@@ -239,14 +253,11 @@ __global__ void __launch_bounds__(kCopyThreads, 4) gather_rows_kernel(const __gr
   }
 }
 
-// ---- TMA (bulk async copy) implementation -----------------------------------------------------------------------
+// ---- hybrid: bulk-async (TMA) rings + LDG warps in one launch ----------------------------------------------------
 
-constexpr int kTmaWarps = 4;
-constexpr int kTmaStages = 6;
-constexpr uint32_t kTmaTile = 8192;  // bytes per bulk copy
-constexpr int kTmaStoresInFlight = 3;
-constexpr uint32_t kTmaSmemBytes = kTmaWarps * kTmaStages * kTmaTile;  // 192 KiB
-constexpr uint32_t kTmaMinRow = 2048;  // rows shorter than this go to the LDG kernel
+constexpr int kHybridWarps = 8;
+constexpr int kMaxTmaStages = 16;
+constexpr uint32_t kTmaMinRow = 2048;  // rows shorter than this stay on the LDG path
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -280,9 +291,18 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+// wait until at most n of this thread's committed bulk groups are still READING shared memory
+__device__ __forceinline__ void bulk_wait_read(uint32_t n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
+  }
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -292,9 +312,9 @@ struct TmaTile {
   uint32_t bytes;
 };
 
-// tile_start / aux here are in units of kTmaTile (aux = tiles per row; every row is tiled on its own).
+// For the bulk class, tile_start / aux are in units of p.tma_tile (aux = tiles per row; rows are tiled one by one).
 __device__ __forceinline__ TmaTile tma_decode(const CopyParams& p, uint32_t t) {
-  uint32_t lo = 0, hi = p.njobs;
+  uint32_t lo = 0, hi = p.n_tma;
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
     if (p.tile_start[mid] <= t) lo = mid; else hi = mid;
@@ -303,51 +323,67 @@ __device__ __forceinline__ TmaTile tma_decode(const CopyParams& p, uint32_t t) {
   const uint32_t lt = t - p.tile_start[lo];
   const uint32_t tpr = p.aux[lo];
   const uint32_t row = lt / tpr;
-  const uint64_t col = (uint64_t)(lt - row * tpr) * kTmaTile;
+  const uint64_t col = (uint64_t)(lt - row * tpr) * p.tma_tile;
   TmaTile r;
   r.src = static_cast<const uint8_t*>(j.src) + (int64_t)row * j.src_pitch + col;
   r.dst = static_cast<uint8_t*>(j.dst) + (int64_t)row * j.dst_pitch + col;
-  r.bytes = (uint32_t)min((uint64_t)kTmaTile, j.row_bytes - col);
+  r.bytes = (uint32_t)min((uint64_t)p.tma_tile, j.row_bytes - col);
   return r;
 }
 
-__global__ void __launch_bounds__(kTmaWarps * 32, 1) copy2d_tma_kernel(const __grid_constant__ CopyParams p) {
+__global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_kernel(const __grid_constant__ CopyParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full[kTmaWarps][kTmaStages];
+  __shared__ __align__(8) uint64_t full[kHybridWarps][kMaxTmaStages];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tma_total = p.tile_start[p.n_tma];
+  if (warp >= p.tma_warps) {
+    // ---- LDG warps: the table's non-bulk jobs (tiles [tma_total, total)) ----
+    const uint32_t total = p.tile_start[p.njobs];
+    const uint32_t nthr = (kHybridWarps - p.tma_warps) * 32;
+    const uint32_t tid = threadIdx.x - p.tma_warps * 32;
+    for (uint32_t t = tma_total + blockIdx.x; t < total; t += gridDim.x) {
+      const uint32_t j = find_job(p, t);
+      run_tile(p.jobs[j], p.mode[j], p.aux[j], t - p.tile_start[j], tid, nthr);
+    }
+    return;
+  }
   if (lane != 0) return;  // one elected lane per warp drives its own independent ring
-  uint8_t* ring = smem + (size_t)warp * kTmaStages * kTmaTile;
-  for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[warp][s], 1);
+  const uint32_t stages = p.tma_stages, tile = p.tma_tile, stores = p.tma_stores;
+  uint8_t* ring = smem + (size_t)warp * stages * tile;
+  for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[warp][s], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
-  const uint32_t total = p.tile_start[p.njobs];
-  const uint32_t nworkers = gridDim.x * kTmaWarps;
-  const uint32_t w = blockIdx.x * kTmaWarps + warp;
-  if (w >= total) return;
-  const uint32_t mine = (total - w + nworkers - 1) / nworkers;  // tiles w, w+nworkers, ...
+  const uint32_t nworkers = gridDim.x * p.tma_warps;
+  const uint32_t w = blockIdx.x * p.tma_warps + warp;
+  if (w >= tma_total) return;
+  const uint32_t mine = (tma_total - w + nworkers - 1) / nworkers;  // tiles w, w+nworkers, ...
 
-  // Loads run kTmaStages - kTmaStoresInFlight tiles ahead of the stores.
-  constexpr int kAhead = kTmaStages - kTmaStoresInFlight;
-  uint32_t issued = 0;
-  auto issue_load = [&](uint32_t k) {
-    const TmaTile tl = tma_decode(p, w + k * nworkers);
-    const uint32_t s = k % kTmaStages;
-    mbar_expect_tx(&full[warp][s], tl.bytes);
-    bulk_g2s(ring + (size_t)s * kTmaTile, tl.src, tl.bytes, &full[warp][s]);
+  // Loads run (stages - stores) tiles ahead of the stores.
+  const uint32_t ahead = stages - stores;
+  uint32_t issued = 0, ld_stage = 0;
+  auto issue_load = [&]() {
+    const TmaTile tl = tma_decode(p, w + issued * nworkers);
+    mbar_expect_tx(&full[warp][ld_stage], tl.bytes);
+    bulk_g2s(ring + (size_t)ld_stage * tile, tl.src, tl.bytes, &full[warp][ld_stage]);
+    ++issued;
+    if (++ld_stage == stages) ld_stage = 0;
   };
-  for (; issued < mine && issued < (uint32_t)kAhead; ++issued) issue_load(issued);
+  while (issued < mine && issued < ahead) issue_load();
+  uint32_t st_stage = 0, parity = 0;
   for (uint32_t k = 0; k < mine; ++k) {
-    const uint32_t s = k % kTmaStages;
     const TmaTile tl = tma_decode(p, w + k * nworkers);
-    mbar_wait(&full[warp][s], (k / kTmaStages) & 1u);
-    bulk_s2g(tl.dst, ring + (size_t)s * kTmaTile, tl.bytes);
+    mbar_wait(&full[warp][st_stage], parity);
+    bulk_s2g(tl.dst, ring + (size_t)st_stage * tile, tl.bytes);
+    if (++st_stage == stages) {
+      st_stage = 0;
+      parity ^= 1u;
+    }
     if (issued < mine) {
-      // stage (issued % kTmaStages) was last used by tile issued - kTmaStages = k - kTmaStoresInFlight; its store
-      // group must have finished reading smem, the kTmaStoresInFlight newer groups (k-2, k-1, k) may still be.
-      bulk_wait_read<kTmaStoresInFlight>();
-      issue_load(issued);
-      ++issued;
+      // the stage about to be refilled was last used by tile k - stores; its store group must have finished
+      // reading shared memory, the `stores` newer groups (.., k-1, k) may still be in flight
+      bulk_wait_read(stores);
+      issue_load();
     }
   }
   bulk_wait_all();
@@ -357,24 +393,39 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) copy2d_tma_kernel(const __g
 
 enum CopyImpl { kImplAuto = 0, kImplLdg = 1, kImplTma = 2 };
 
-CopyImpl copy_impl() {
-  static CopyImpl impl = [] {
-    const char* e = std::getenv("MB_COPY_IMPL");
-    if (!e) return kImplAuto;
-    if (!std::strcmp(e, "ldg")) return kImplLdg;
-    if (!std::strcmp(e, "tma")) return kImplTma;
-    return kImplAuto;
-  }();
-  return impl;
+long env_long(const char* name, long dflt, long lo, long hi) {
+  const char* e = std::getenv(name);
+  if (!e || !*e) return dflt;
+  long v = std::strtol(e, nullptr, 0);
+  return v < lo || v > hi ? dflt : v;
 }
 
-int grid_multiplier() {
-  static int m = [] {
-    const char* e = std::getenv("MB_COPY_CTAS_PER_SM");
-    int v = e ? std::atoi(e) : 8;
-    return v > 0 && v <= 32 ? v : 8;
+struct CopyTuning {
+  CopyImpl impl;
+  int ctas_per_sm;        // LDG kernel grid = min(tiles, SMs * ctas_per_sm)
+  uint32_t tma_tile;      // bytes per bulk copy (multiple of 16)
+  uint32_t tma_stages;    // ring depth per warp
+  uint32_t tma_stores;    // store groups in flight per warp
+  uint32_t tma_warps;     // ring-driving warps per CTA (the other 8 - tma_warps warps run the LDG path)
+  uint64_t tma_min_bytes; // auto: use the hybrid kernel when the bulk class carries at least this much
+};
+
+const CopyTuning& tuning() {
+  static const CopyTuning t = [] {
+    CopyTuning c;
+    const char* e = std::getenv("MB_COPY_IMPL");
+    c.impl = !e ? kImplAuto : !std::strcmp(e, "ldg") ? kImplLdg : !std::strcmp(e, "tma") ? kImplTma : kImplAuto;
+    c.ctas_per_sm = (int)env_long("MB_COPY_CTAS_PER_SM", 16, 1, 32);
+    c.tma_tile = (uint32_t)env_long("MB_TMA_TILE", 16384, 512, 65536) & ~15u;
+    c.tma_warps = (uint32_t)env_long("MB_TMA_WARPS", 3, 1, kHybridWarps - 1);
+    c.tma_stages = (uint32_t)env_long("MB_TMA_STAGES", 4, 2, kMaxTmaStages);
+    while ((uint64_t)c.tma_warps * c.tma_stages * c.tma_tile > 200u * 1024u && c.tma_stages > 2) --c.tma_stages;
+    c.tma_stores = (uint32_t)env_long("MB_TMA_STORES", c.tma_stages / 2, 1, 7);
+    if (c.tma_stores >= c.tma_stages) c.tma_stores = c.tma_stages - 1;
+    c.tma_min_bytes = (uint64_t)env_long("MB_TMA_MIN_BYTES", 1l << 20, 0, 1l << 40);
+    return c;
   }();
-  return m;
+  return t;
 }
 
 inline bool aligned16(uint64_t v) { return (v & 15u) == 0; }
@@ -392,14 +443,18 @@ int validate_job(const mb_copy_job& j, int i) {
   return MB_OK;
 }
 
-std::once_flag g_tma_attr_once;
-cudaError_t g_tma_attr_err = cudaSuccess;
+std::mutex g_attr_mu;
+uint32_t g_hybrid_smem_set = 0;
 
-int launch_chunk(const mb_copy_job* jobs, int n, bool allow_tma, cudaStream_t stream) {
+int launch_chunk(const mb_copy_job* jobs, int n, cudaStream_t stream) {
+  const CopyTuning& tn = tuning();
   CopyParams p;
   std::memset(&p, 0, sizeof(p));
-  bool tma = allow_tma;
+  // normalise, then order the bulk-async class first
+  mb_copy_job norm[kMaxJobs];
+  bool bulk[kMaxJobs];
   uint32_t nj = 0;
+  uint64_t bulk_bytes = 0;
   for (int i = 0; i < n; ++i) {
     if (jobs[i].rows == 0 || jobs[i].row_bytes == 0) continue;
     mb_copy_job j = jobs[i];
@@ -407,18 +462,34 @@ int launch_chunk(const mb_copy_job* jobs, int n, bool allow_tma, cudaStream_t st
       j.row_bytes *= j.rows;  // contiguous on both sides: one long row
       j.rows = 1;
     }
-    p.jobs[nj++] = j;
-    tma = tma && job_tma_ok(j);
+    bulk[nj] = tn.impl != kImplLdg && job_tma_ok(j);
+    if (bulk[nj]) bulk_bytes += j.rows * j.row_bytes;
+    norm[nj++] = j;
   }
   if (nj == 0) return 0;
+  const bool hybrid = bulk_bytes > 0 && (tn.impl == kImplTma || bulk_bytes >= tn.tma_min_bytes);
+  uint32_t k = 0;
+  if (hybrid) {
+    for (uint32_t i = 0; i < nj; ++i)
+      if (bulk[i]) { p.jobs[k] = norm[i]; p.mode[k++] = kModeTma; }
+    p.n_tma = k;
+    for (uint32_t i = 0; i < nj; ++i)
+      if (!bulk[i]) p.jobs[k++] = norm[i];
+  } else {
+    for (uint32_t i = 0; i < nj; ++i) p.jobs[k++] = norm[i];
+  }
   p.njobs = nj;
+  p.tma_tile = tn.tma_tile;
+  p.tma_warps = (uint16_t)tn.tma_warps;
+  p.tma_stages = (uint8_t)tn.tma_stages;
+  p.tma_stores = (uint8_t)tn.tma_stores;
   uint64_t tiles = 0;
   for (uint32_t i = 0; i < nj; ++i) {
     const mb_copy_job& j = p.jobs[i];
     p.tile_start[i] = (uint32_t)tiles;
     uint64_t t;
-    if (tma) {
-      const uint64_t tpr = (j.row_bytes + kTmaTile - 1) / kTmaTile;
+    if (i < p.n_tma) {
+      const uint64_t tpr = (j.row_bytes + tn.tma_tile - 1) / tn.tma_tile;
       p.aux[i] = (uint32_t)tpr;
       t = tpr * j.rows;
     } else if (j.row_bytes >= kTileBytes) {
@@ -443,17 +514,21 @@ int launch_chunk(const mb_copy_job* jobs, int n, bool allow_tma, cudaStream_t st
   p.tile_start[nj] = (uint32_t)tiles;
   const int sms = sm_count(current_device());
   if (sms <= 0) return MB_ECUDA;
-  if (tma) {
-    std::call_once(g_tma_attr_once, [] {
-      g_tma_attr_err = cudaFuncSetAttribute(copy2d_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)kTmaSmemBytes);
-    });
-    MB_CUDA(g_tma_attr_err);
-    const uint32_t want = (uint32_t)((tiles + kTmaWarps - 1) / kTmaWarps);
-    const uint32_t grid = std::min<uint32_t>(want, (uint32_t)sms);
-    copy2d_tma_kernel<<<grid, kTmaWarps * 32, kTmaSmemBytes, stream>>>(p);
+  if (hybrid) {
+    const uint32_t smem = tn.tma_warps * tn.tma_stages * tn.tma_tile;
+    {
+      std::lock_guard<std::mutex> l(g_attr_mu);
+      if (g_hybrid_smem_set < smem) {
+        MB_CUDA(cudaFuncSetAttribute(copy2d_hybrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_hybrid_smem_set = smem;
+      }
+    }
+    const uint64_t tma_tiles = p.tile_start[p.n_tma];
+    const uint64_t want = std::max<uint64_t>((tma_tiles + tn.tma_warps - 1) / tn.tma_warps, tiles - tma_tiles);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms);
+    copy2d_hybrid_kernel<<<grid, kHybridWarps * 32, smem, stream>>>(p);
   } else {
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)sms * grid_multiplier());
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)sms * tn.ctas_per_sm);
     copy2d_ldg_kernel<<<grid, kCopyThreads, 0, stream>>>(p);
   }
   MB_CUDA(cudaGetLastError());
@@ -474,14 +549,9 @@ int mb_copy2d_batch(const mb_copy_job* jobs, int njobs, mb_stream_t stream_) {
     int rc = validate_job(jobs[i], i);
     if (rc) return rc;
   }
-  const CopyImpl impl = copy_impl();
-  // auto: TMA only pays when there is enough to stream; tiny tables are launch-latency bound either way.
-  uint64_t total = 0;
-  for (int i = 0; i < njobs; ++i) total += jobs[i].rows * jobs[i].row_bytes;
-  const bool allow_tma = impl == kImplTma || (impl == kImplAuto && total >= (8ull << 20));
   int launches = 0;
   for (int i = 0; i < njobs; i += kMaxJobs) {
-    int rc = launch_chunk(jobs + i, std::min(kMaxJobs, njobs - i), allow_tma, stream);
+    int rc = launch_chunk(jobs + i, std::min(kMaxJobs, njobs - i), stream);
     if (rc < 0) return rc;
     launches += rc;
   }
@@ -514,7 +584,7 @@ int mb_gather_rows(void* dst, uint64_t dst_pitch, const void* const* src_rows_de
   p.total_tiles = (uint32_t)tiles;
   const int sms = sm_count(current_device());
   if (sms <= 0) return MB_ECUDA;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)sms * grid_multiplier());
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)sms * tuning().ctas_per_sm);
   gather_rows_kernel<<<grid, kCopyThreads, 0, static_cast<cudaStream_t>(stream_)>>>(p);
   MB_CUDA(cudaGetLastError());
   return 1;
