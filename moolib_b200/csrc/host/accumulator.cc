@@ -1,0 +1,808 @@
+// Accumulator (HP-A host side): moolib's gradient accumulation / model-sync state machine with the data plane replaced
+// by the sm_100a kernels.
+//
+// Mirrors AccumulatorImpl (reference: src/accumulator.cc:150-1192; bound at src/moolib.cc:1695-1862): same methods, same
+// asynchronous contract (results are applied only inside update(), src/accumulator.cc:508-551), same virtual-batch gate
+// (count allreduce, :1035-1078), leader election by max (modelVersion, name) (:581-625), late-joiner model/state sync
+// (:464-488, :719-836).  What changes for CUDA parameters:
+//   reduce_gradients(): ONE stage launch (K-A1: staging (=|+=) grads, grads <- 0) instead of 36 D2H copy_ + 36 zero_
+//                       (:941-980, :410-418); no stream synchronize (:937) -- everything stays stream-ordered.
+//   when the count gate opens: ONE allreduce launch (K-A2) that pulls every peer's staging over NVLink, sums in rank
+//                       order, multiplies by 1.0f/numGradients and writes the .grad tensors -- instead of the RPC tree
+//                       (src/group.h:570-654), 36 H2D copy_ and 36 mul_ (:441-442) and a stream synchronize (:450).
+// CPU parameters (BASELINE.json config 0, "plumbing, no GPU") reduce over the control plane in member order.
+#include "common.h"
+#include "control.h"
+#include "device_reduce.h"
+
+#include <ATen/ATen.h>
+#include <cuda_runtime_api.h>
+
+namespace mbh {
+
+namespace {
+
+struct ReduceSlot {
+  size_t index = 0;
+  uint32_t syncId = 0;
+  mb_ar_hdr data{0, 0, 0, 0};  // numGradients, numSkipped, batchSize, has_grads (something is staged)
+  bool isCounting = false, wantsMoreCounting = false, wantsReduce = false, reduceStarted = false, reduceDone = false;
+  std::shared_ptr<SmallReduce> countOp;
+  std::shared_ptr<SmallReduce> reduceOp;   // CPU-parameter path
+  std::vector<torch::Tensor> cpuStaging;   // CPU-parameter path (src/accumulator.cc:847-874)
+  cudaEvent_t event = nullptr;             // device path: completion of the K-A2 launch
+  bool kernelInFlight = false;
+  Clock::time_point reduceStart;
+  ~ReduceSlot() {
+    if (event) cudaEventDestroy(event);
+  }
+};
+
+Bytes packU64(uint64_t v) {
+  Writer w;
+  w.u64(v);
+  return w.b;
+}
+
+// CPU-path payload = AccumulatorReductionType (src/group.h:195-218)
+Bytes packReduction(const mb_ar_hdr& h, const std::vector<torch::Tensor>& grads) {
+  Writer w;
+  w.u64(h.num_gradients);
+  w.u64(h.num_skipped);
+  w.u64(h.batch_size);
+  w.u32((uint32_t)grads.size());
+  for (auto& g : grads) w.str(packTensor(g));
+  return w.b;
+}
+struct Reduction {
+  mb_ar_hdr h{0, 0, 0, 0};
+  std::vector<torch::Tensor> grads;
+};
+Reduction unpackReduction(const Bytes& b) {
+  Reader r(b);
+  Reduction x;
+  x.h.num_gradients = r.u64();
+  x.h.num_skipped = r.u64();
+  x.h.batch_size = r.u64();
+  uint32_t n = r.u32();
+  for (uint32_t i = 0; i < n; ++i) x.grads.push_back(unpackTensor(r.str()));
+  return x;
+}
+// AccumulatorReductionType::add (src/group.h:201-212)
+Bytes addReductions(const Bytes& a, const Bytes& b) {
+  Reduction x = unpackReduction(a), n = unpackReduction(b);
+  if (n.grads.size() == x.grads.size()) {
+    for (size_t i = 0; i < x.grads.size(); ++i) x.grads[i] += n.grads[i];
+  } else if (n.grads.size() > x.grads.size()) {
+    std::swap(x.grads, n.grads);
+  }
+  x.h.num_gradients += n.h.num_gradients;
+  x.h.num_skipped += n.h.num_skipped;
+  x.h.batch_size += n.h.batch_size;
+  return packReduction(x.h, x.grads);
+}
+
+py::object deepCopyToCpu(const py::handle& v) {
+  if (py::isinstance<py::dict>(v)) {
+    py::dict d;
+    for (auto kv : py::reinterpret_borrow<py::dict>(v)) d[deepCopyToCpu(kv.first)] = deepCopyToCpu(kv.second);
+    return std::move(d);
+  }
+  if (py::isinstance<py::list>(v)) {
+    py::list src = py::reinterpret_borrow<py::list>(v), dst(src.size());
+    for (size_t i = 0; i < src.size(); ++i) dst[i] = deepCopyToCpu(src[i]);
+    return std::move(dst);
+  }
+  if (is_tensor(v)) return to_python(to_tensor(v).to(torch::kCPU, /*non_blocking=*/false, /*copy=*/true));
+  if (py::isinstance<py::tuple>(v)) {
+    py::tuple src = py::reinterpret_borrow<py::tuple>(v), dst(src.size());
+    for (size_t i = 0; i < src.size(); ++i) dst[i] = deepCopyToCpu(src[i]);
+    return std::move(dst);
+  }
+  return py::reinterpret_borrow<py::object>(v);
+}
+
+}  // namespace
+
+class Accumulator {
+ public:
+  Accumulator(std::string name, py::object parameters, py::object buffers, py::object group) {
+    if (group.is_none()) {
+      shouldUpdateGroup_ = true;
+      ownGroup_ = makeOwnGroup(name);
+      parts_ = groupPartsOf(ownGroup_);
+      resName_ = name + "::accumulator";
+    } else {
+      ownGroup_ = group;
+      parts_ = groupPartsOf(group);
+      resName_ = parts_.info->name + "::" + name;
+    }
+    myName_ = parts_.rpc->getName();
+    slots_.resize(1);
+    for (auto v : parameters) {
+      if (!is_tensor(v)) throw std::runtime_error("Accumulator parameter is not a Tensor!");
+      torch::Tensor t = to_tensor(v);
+      gradsOnCuda_ |= t.is_cuda();
+      if (t.is_cuda()) device_ = t.get_device();
+      params_.push_back(t);
+    }
+    for (auto v : buffers) {
+      if (!is_tensor(v)) throw std::runtime_error("Accumulator buffer is not a Tensor!");
+      buffers_.push_back(to_tensor(v));
+    }
+    if (gradsOnCuda_) {
+      for (auto& p : params_) {
+        if (!p.requires_grad()) continue;
+        if (!p.is_cuda() || p.get_device() != device_ || p.scalar_type() != torch::kFloat32)
+          throw std::runtime_error(
+              "moolib_b200.Accumulator: CUDA parameters must all be float32 on one device (the NVLink allreduce sums "
+              "fp32 like the reference's ATen add)");
+      }
+    }
+    ensureGrads();
+    setupHandlers();
+  }
+
+  ~Accumulator() {
+    parts_.rpc->unhandle("Acc::requestModel/" + resName_);
+    parts_.rpc->unhandle("Acc::modelUpdate/" + resName_);
+    parts_.rpc->unhandle("Acc::buffersUpdate/" + resName_);
+  }
+
+  void connect(const std::string& address) { parts_.rpc->connect(address); }
+
+  // ---- predicates (src/accumulator.cc:372-405) -------------------------------------------------------------------
+  bool connectedImpl() {
+    bool groupActive;
+    {
+      std::lock_guard<std::mutex> l(parts_.info->mutex);
+      groupActive = !parts_.info->members.empty();
+    }
+    return groupActive && !members_.empty() && (hasReceivedModel_ || syncLeader_ == myName_);
+  }
+  bool connected() {
+    std::lock_guard<std::mutex> l(mu_);
+    return connectedImpl();
+  }
+  bool wantsState() {
+    std::lock_guard<std::mutex> l(mu_);
+    return wantsUserState_;
+  }
+  bool hasNewState() { return hasNewUserState_; }
+  bool hasGradients() {
+    std::lock_guard<std::mutex> l(mu_);
+    return hasGradients_;
+  }
+  bool wantsGradientsAtIndex(size_t i) {
+    auto& v = slots_.at(i);
+    return !v || v->reduceDone || !v->reduceStarted;
+  }
+  bool wantsGradientsLocked() {
+    return connectedImpl() && wantsGradientsAtIndex(nextIndex_) && !isWaitingForModel_ && !isFindingLeader_ &&
+           !hasGradients_ && (!gradsOnCuda_ || reducerReady_);
+  }
+  bool wantsGradients() {
+    std::lock_guard<std::mutex> l(mu_);
+    return wantsGradientsLocked();
+  }
+
+  // ---- gradients -------------------------------------------------------------------------------------------------
+  // .grad of every parameter that requires grad, created (zeros) if missing (src/accumulator.cc:857-866)
+  std::vector<torch::Tensor> ensureGrads() {
+    torch::NoGradGuard ng;
+    std::vector<torch::Tensor> r;
+    for (auto& p : params_) {
+      if (!p.requires_grad()) continue;
+      torch::Tensor g = p.mutable_grad();
+      if (!g.defined()) {
+        g = torch::zeros_like(p);
+        p.mutable_grad() = g;
+      }
+      if (gradsOnCuda_ && (!g.is_contiguous() || g.scalar_type() != torch::kFloat32)) {
+        g = g.contiguous().to(torch::kFloat32);
+        p.mutable_grad() = g;
+      }
+      r.push_back(g);
+    }
+    return r;
+  }
+
+  void actuallyZeroGradients() {
+    torch::NoGradGuard ng;
+    std::vector<torch::Tensor> gs;
+    for (auto& p : params_) {
+      torch::Tensor g = p.mutable_grad();
+      if (g.defined()) {
+        g.detach_();
+        gs.push_back(g);
+      }
+    }
+    if (!gs.empty()) at::_foreach_zero_(gs);
+  }
+
+  void zeroGradients() {
+    std::lock_guard<std::mutex> l(mu_);
+    hasGradients_ = false;
+    actuallyZeroGradients();
+  }
+
+  uint64_t flatBytes(const std::vector<torch::Tensor>& gs) {
+    std::vector<uint64_t> n;
+    for (auto& g : gs) n.push_back((uint64_t)g.numel());
+    return mb_ar_flat_numel(n.data(), (int)n.size()) * 4;
+  }
+
+  std::shared_ptr<DeviceReducer> reducer() {
+    if (!reducer_) {
+      auto gs = ensureGrads();
+      reducer_ = parts_.reducers->get("acc/" + resName_, device_, std::max<uint64_t>(flatBytes(gs), 16), (int)slots_.size());
+    }
+    return reducer_;
+  }
+
+  // reference: reduceImpl, src/accumulator.cc:880-1003
+  void reduceImpl(int batchSize) {
+    std::lock_guard<std::mutex> l(mu_);
+    if (!wantsGradientsLocked())
+      throw std::runtime_error("reduceGradients/skipGradients called while wantsGradients() is false");
+    size_t index = nextIndex_;
+    std::shared_ptr<ReduceSlot> target = slots_[index];
+    if (target && target->reduceStarted && !target->reduceDone)
+      throw std::runtime_error("reduceImpl internal error, reduce already started!");
+    if (!target || target->reduceDone) {
+      target = slots_[index] = std::make_shared<ReduceSlot>();
+      target->index = index;
+    }
+    nextIndex_ = (nextIndex_ == slots_.size() - 1) ? 0 : nextIndex_ + 1;
+    target->syncId = hSyncId_;
+    torch::NoGradGuard ng;
+    if (batchSize) {
+      ++target->data.num_gradients;
+      target->data.batch_size += (uint64_t)batchSize;
+      auto gs = ensureGrads();
+      const bool add = target->data.has_grads != 0;
+      if (gradsOnCuda_) {
+        // K-A1: staging (=|+=) grads and grads <- 0 in one launch, ordered after backward() on the current stream
+        std::vector<const float*> ptrs;
+        std::vector<uint64_t> numel;
+        for (auto& g : gs) {
+          ptrs.push_back(g.data_ptr<float>());
+          numel.push_back((uint64_t)g.numel());
+        }
+        c10::cuda::CUDAGuard dg(device_);
+        launch_counter() += check(mb_ar_stage(reducer()->ctx(), (int)index, ptrs.data(), numel.data(), (int)gs.size(),
+                                              add ? 1 : 0, /*zero_src=*/1, current_stream(device_)),
+                                  "Accumulator.reduce_gradients");
+      } else {
+        if (!add) {
+          target->cpuStaging.clear();
+          for (auto& g : gs) target->cpuStaging.push_back(g.detach().clone());
+        } else {
+          for (size_t i = 0; i < gs.size(); ++i) target->cpuStaging[i].add_(gs[i]);
+        }
+        actuallyZeroGradients();
+      }
+      target->data.has_grads = 1;
+    } else {
+      ++target->data.num_skipped;
+    }
+    if (target->syncId == hSyncId_ && target->syncId == parts_.info->syncId.load()) {
+      if (target->isCounting) target->wantsMoreCounting = true;
+      else startCount(target);
+    }
+  }
+  void reduceGradients(int batchSize) { reduceImpl(batchSize); }
+  void skipGradients() { reduceImpl(0); }
+
+  // reference: startCount, src/accumulator.cc:1035-1078
+  void startCount(const std::shared_ptr<ReduceSlot>& target) {
+    if (target->syncId != hSyncId_ || target->syncId != parts_.info->syncId.load()) return;
+    target->isCounting = true;
+    try {
+      target->countOp = parts_.service->allReduce(
+          parts_.info, "Accumulator reduce size " + std::to_string(target->index) + "/" + resName_,
+          packU64(target->data.batch_size), [](const Bytes& a, const Bytes& b) {
+            Reader ra(a), rb(b);
+            return packU64(ra.u64() + rb.u64());
+          });
+    } catch (const std::exception&) {
+      target->isCounting = false;
+      onError();
+    }
+  }
+
+  // reference: startReduce, src/accumulator.cc:1005-1033
+  void startReduce(const std::shared_ptr<ReduceSlot>& target) {
+    if (target->syncId != hSyncId_ || target->syncId != parts_.info->syncId.load()) return;
+    target->reduceStarted = true;
+    target->reduceStart = Clock::now();
+    torch::NoGradGuard ng;
+    if (gradsOnCuda_) {
+      auto gs = ensureGrads();
+      std::vector<float*> ptrs;
+      std::vector<uint64_t> numel;
+      for (auto& g : gs) {
+        ptrs.push_back(g.data_ptr<float>());
+        numel.push_back((uint64_t)g.numel());
+      }
+      c10::cuda::CUDAGuard dg(device_);
+      auto stream = c10::cuda::getCurrentCUDAStream(device_);
+      // K-A2: barrier + P2P reduce + 1/numGradients scale + scatter into the .grad tensors, one launch
+      launch_counter() += check(
+          mb_ar_allreduce(reducer()->ctx(), (int)target->index, &target->data, ptrs.data(), numel.data(), (int)gs.size(),
+                          nullptr, 0, /*scale=*/1, MB_AR_ALGO_AUTO, (uint32_t)(parts_.rpc->getTimeout() * 1000),
+                          static_cast<mb_stream_t>(stream.stream())),
+          "Accumulator allreduce");
+      if (!target->event) cudaEventCreateWithFlags(&target->event, cudaEventDisableTiming);
+      cudaEventRecord(target->event, stream.stream());
+      target->kernelInFlight = true;
+    } else {
+      try {
+        target->reduceOp = parts_.service->allReduce(
+            parts_.info, "Accumulator reduce " + std::to_string(target->index) + "/" + resName_,
+            packReduction(target->data, target->data.has_grads ? target->cpuStaging : std::vector<torch::Tensor>{}),
+            addReductions);
+      } catch (const std::exception&) {
+        onError();
+      }
+    }
+  }
+
+  // reference: setGradients, src/accumulator.cc:425-462 (CPU path; on the device path the kernel already did it)
+  void finishReduce(const std::shared_ptr<ReduceSlot>& target, const mb_ar_hdr& total) {
+    target->reduceDone = true;
+    ++modelVersion_;
+    stats_ = total;
+    hasGradients_ = true;
+  }
+
+  // Runs the pending "result closure" of the slot whose turn it is; reference: checkGradientResultCallback (:508-517)
+  void checkGradientResult() {
+    auto& v = slots_[nextResultIndex_];
+    if (!v) return;
+    bool ran = false;
+    if (v->countOp && v->countOp->future->done()) {
+      auto op = std::move(v->countOp);
+      v->countOp.reset();
+      ran = true;
+      std::lock_guard<std::mutex> fl(op->future->mu);
+      if (op->future->flags & 1) {
+        Reader r(op->future->value);
+        uint64_t size = r.u64();
+        if (size >= virtualBatchSize_) {
+          if (v->syncId == hSyncId_ && v->syncId == parts_.info->syncId.load()) {
+            v->wantsReduce = true;
+            startReduce(v);
+          }
+        } else {
+          v->isCounting = false;
+          if (v->wantsMoreCounting) startCount(v);
+        }
+      } else {
+        onError();
+      }
+    } else if (v->kernelInFlight) {
+      cudaError_t e = cudaEventQuery(v->event);
+      if (e != cudaErrorNotReady) {
+        v->kernelInFlight = false;
+        ran = true;
+        mb_ar_hdr total;
+        int status = 0;
+        mb_ar_result(reducer()->ctx(), (int)v->index, &total, &status);
+        if (e != cudaSuccess || status != 0) {
+          lastError_ = e != cudaSuccess ? std::string(cudaGetErrorString(e))
+                                        : (status == MB_ETIMEOUT ? "allreduce barrier timed out" : "allreduce failed");
+          v->reduceDone = true;  // abandon the round; the resync resets the slots
+          onError();
+        } else {
+          finishReduce(v, total);
+        }
+      }
+    } else if (v->reduceOp && v->reduceOp->future->done()) {
+      auto op = std::move(v->reduceOp);
+      v->reduceOp.reset();
+      ran = true;
+      std::lock_guard<std::mutex> fl(op->future->mu);
+      if (op->future->flags & 1) {
+        torch::NoGradGuard ng;
+        Reduction red = unpackReduction(op->future->value);
+        if (red.grads.empty()) {
+          actuallyZeroGradients();
+        } else if (red.h.num_gradients) {
+          auto gs = ensureGrads();
+          if (gs.size() != red.grads.size()) throw std::runtime_error("grads shrank?");
+          for (size_t i = 0; i < gs.size(); ++i) {
+            gs[i].copy_(red.grads[i], true);
+            gs[i].mul_(1.0f / red.h.num_gradients);
+          }
+        }
+        red.h.has_grads = red.grads.empty() ? 0 : 1;
+        finishReduce(v, red.h);
+      } else {
+        onError();
+      }
+    }
+    if (ran) nextResultIndex_ = (nextResultIndex_ == slots_.size() - 1) ? 0 : nextResultIndex_ + 1;
+  }
+
+  void onError() {
+    if (hSyncId_ == parts_.info->syncId.load()) resync();
+  }
+  void resync() {
+    std::lock_guard<std::mutex> l(parts_.info->mutex);
+    parts_.service->resync(*parts_.info);
+  }
+
+  // ---- model / state sync (src/accumulator.cc:464-488, 713-836) --------------------------------------------------
+  void setupHandlers() {
+    parts_.rpc->handle("Acc::requestModel/" + resName_, [this](const std::string&, const Bytes& p) {
+      Reader r(p);
+      uint32_t syncId = r.u32();
+      std::string peer = r.str();
+      std::lock_guard<std::mutex> l(netMu_);
+      if (syncId != netSyncId_) return;
+      if (std::find(requestedModelUpdate_.begin(), requestedModelUpdate_.end(), peer) == requestedModelUpdate_.end())
+        requestedModelUpdate_.push_back(peer);
+    });
+    parts_.rpc->handle("Acc::modelUpdate/" + resName_, [this](const std::string&, const Bytes& p) {
+      Reader r(p);
+      uint32_t syncId = r.u32();
+      bool regular = r.u32() != 0;
+      int64_t version = r.i64();
+      uint32_t np = r.u32();
+      std::vector<Bytes> ps(np);
+      for (auto& x : ps) x = r.str();
+      uint32_t nb = r.u32();
+      std::vector<Bytes> bs(nb);
+      for (auto& x : bs) x = r.str();
+      Bytes state = r.str();
+      std::lock_guard<std::mutex> l(netMu_);
+      if (syncId != netSyncId_) return;
+      if (regular && version != netModelVersion_ && !netWaitingForModel_) return;
+      if (np != params_.size() || nb != buffers_.size()) return;
+      newParameters_ = std::move(ps);
+      newBuffers_ = std::move(bs);
+      newUserState_ = std::move(state);
+      newModelVersion_ = version;
+      haveNewParameters_ = true;
+    });
+    parts_.rpc->handle("Acc::buffersUpdate/" + resName_, [this](const std::string&, const Bytes& p) {
+      Reader r(p);
+      uint32_t syncId = r.u32();
+      uint32_t nb = r.u32();
+      std::vector<Bytes> bs(nb);
+      for (auto& x : bs) x = r.str();
+      std::lock_guard<std::mutex> l(netMu_);
+      if (syncId != netSyncId_ || nb != buffers_.size()) return;
+      newBuffers_ = std::move(bs);
+      haveNewBuffers_ = true;
+    });
+  }
+
+  void requestModel() {
+    if (syncLeader_ == myName_) return;
+    isWaitingForModel_ = true;
+    isWaitingForModelTimestamp_ = Clock::now();
+    Writer w;
+    w.u32(hSyncId_);
+    w.str(myName_);
+    parts_.rpc->send(syncLeader_, "Acc::requestModel/" + resName_, w.b);
+  }
+
+  Bytes packModel(bool regular, const Bytes& state) {
+    torch::NoGradGuard ng;
+    Writer w;
+    w.u32(hSyncId_);
+    w.u32(regular ? 1 : 0);
+    w.i64(modelVersion_);
+    w.u32((uint32_t)params_.size());
+    for (auto& p : params_) w.str(packTensor(p.detach().to(torch::kCPU)));
+    w.u32((uint32_t)buffers_.size());
+    for (auto& b : buffers_) w.str(packTensor(b.detach().to(torch::kCPU)));
+    w.str(state);
+    return w.b;
+  }
+
+  void setState(py::object userState) {
+    userState = deepCopyToCpu(userState);
+    Bytes pickled = pickleDumps(userState);
+    std::lock_guard<std::mutex> l(mu_);
+    userState_ = userState;
+    wantsUserState_ = false;
+    auto now = Clock::now();
+    std::vector<std::string> requested;
+    {
+      std::lock_guard<std::mutex> nl(netMu_);
+      requested.swap(requestedModelUpdate_);
+    }
+    Bytes msg;
+    for (auto& n : requested) {
+      if (n != myName_ && std::find(members_.begin(), members_.end(), n) != members_.end()) {
+        if (msg.empty()) msg = packModel(false, pickled);
+        parts_.rpc->send(n, "Acc::modelUpdate/" + resName_, msg);
+      }
+    }
+    if (syncLeader_ == myName_ && now - lastSentModel_ >= std::chrono::seconds(600)) {
+      lastSentModel_ = now;
+      Bytes reg = packModel(true, pickled);
+      for (auto& n : members_)
+        if (n != myName_) parts_.rpc->send(n, "Acc::modelUpdate/" + resName_, reg);
+    }
+  }
+
+  py::object state() {
+    std::lock_guard<std::mutex> l(mu_);
+    hasNewUserState_ = false;
+    return userState_ ? *userState_ : py::none();
+  }
+
+  void sendModelUpdates() {
+    if (syncLeader_ != myName_) {
+      wantsUserState_ = false;
+      std::lock_guard<std::mutex> nl(netMu_);
+      requestedModelUpdate_.clear();
+      return;
+    }
+    auto now = Clock::now();
+    bool requested;
+    {
+      std::lock_guard<std::mutex> nl(netMu_);
+      requested = !requestedModelUpdate_.empty();
+    }
+    if (requested || now - lastSentModel_ >= std::chrono::seconds(600)) wantsUserState_ = true;
+    if (now - lastSentBuffers_ >= std::chrono::seconds(12) && !buffers_.empty()) {
+      lastSentBuffers_ = now;
+      torch::NoGradGuard ng;
+      Writer w;
+      w.u32(hSyncId_);
+      w.u32((uint32_t)buffers_.size());
+      for (auto& b : buffers_) w.str(packTensor(b.detach().to(torch::kCPU)));
+      for (auto& n : members_)
+        if (n != myName_) parts_.rpc->send(n, "Acc::buffersUpdate/" + resName_, w.b);
+    }
+  }
+
+  void commitModelUpdate() {
+    torch::NoGradGuard ng;
+    std::vector<Bytes> ps, bs;
+    Bytes state;
+    {
+      std::lock_guard<std::mutex> nl(netMu_);
+      haveNewParameters_ = false;
+      haveNewBuffers_ = false;
+      modelVersion_ = newModelVersion_;
+      ps.swap(newParameters_);
+      bs.swap(newBuffers_);
+      state.swap(newUserState_);
+    }
+    lastReceivedModel_ = Clock::now();
+    if (ps.size() != params_.size()) throw std::runtime_error("Model parameters size mismatch in update!");
+    if (bs.size() != buffers_.size()) throw std::runtime_error("Model parameters size mismatch in update!");
+    for (size_t i = 0; i < params_.size(); ++i) params_[i].copy_(unpackTensor(ps[i]).view_as(params_[i]), true);
+    for (size_t i = 0; i < buffers_.size(); ++i) buffers_[i].copy_(unpackTensor(bs[i]).view_as(buffers_[i]), true);
+    userState_ = pickleLoads(state);
+    hasNewUserState_ = true;
+    hasReceivedModel_ = true;
+  }
+
+  void commitBuffersUpdate() {
+    torch::NoGradGuard ng;
+    std::vector<Bytes> bs;
+    {
+      std::lock_guard<std::mutex> nl(netMu_);
+      haveNewBuffers_ = false;
+      bs.swap(newBuffers_);
+    }
+    if (bs.size() != buffers_.size()) throw std::runtime_error("Model buffers size mismatch in update!");
+    for (size_t i = 0; i < buffers_.size(); ++i) buffers_[i].copy_(unpackTensor(bs[i]).view_as(buffers_[i]), true);
+  }
+
+  // ---- update (src/accumulator.cc:519-665) -------------------------------------------------------------------------
+  void update() {
+    torch::NoGradGuard ng;
+    if (shouldUpdateGroup_) {
+      py::gil_scoped_release nogil;
+      parts_.service->update(*parts_.info, 0, 10 * 1000);
+    }
+    std::lock_guard<std::mutex> l(mu_);
+    auto now = Clock::now();
+
+    // leader election result
+    if (findLeaderOp_ && findLeaderOp_->future->done()) {
+      auto op = std::move(findLeaderOp_);
+      findLeaderOp_.reset();
+      std::lock_guard<std::mutex> fl(op->future->mu);
+      if (op->future->flags & 1) {
+        Reader r(op->future->value);
+        int64_t version = r.i64();
+        std::string leader = r.str();
+        isFindingLeader_ = false;
+        syncLeader_ = leader;
+        {
+          std::lock_guard<std::mutex> gl(parts_.info->mutex);
+          members_ = parts_.info->members;
+        }
+        if (version != modelVersion_ || !hasReceivedModel_) requestModel();
+        else lastReceivedModel_ = now;
+      } else if (hSyncId_ == parts_.info->syncId.load()) {
+        resync();
+      }
+    }
+    if (gradsOnCuda_ && hSyncId_ != 0 && !reducerReady_) {
+      auto r = reducer();
+      if (r->failed()) throw std::runtime_error(r->error());
+      reducerReady_ = r->poll() && r->syncId() == hSyncId_;
+    }
+    checkGradientResult();
+
+    uint32_t groupSync = parts_.info->syncId.load();
+    if (hSyncId_ != groupSync) {
+      hSyncId_ = groupSync;
+      syncLeader_.clear();
+      findLeaderOp_.reset();
+      for (auto& v : slots_) v.reset();
+      nextIndex_ = nextResultIndex_ = 0;
+      {
+        std::lock_guard<std::mutex> nl(netMu_);
+        netSyncId_ = hSyncId_;
+        requestedModelUpdate_.clear();
+        haveNewParameters_ = false;
+      }
+      hasNewUserState_ = false;
+      wantsUserState_ = false;
+      isFindingLeader_ = true;
+      isWaitingForModel_ = false;
+      hasGradients_ = false;
+      reducerReady_ = false;
+      members_.clear();
+      if (hSyncId_ != 0) {
+        Writer w;
+        w.i64(modelVersion_);
+        w.str(myName_);
+        try {
+          // max over (modelVersion, name) (src/accumulator.cc:589-596)
+          findLeaderOp_ = parts_.service->allReduce(
+              parts_.info, "Accumulator::findLeader/" + resName_, w.b, [](const Bytes& a, const Bytes& b) {
+                Reader ra(a), rb(b);
+                int64_t va = ra.i64(), vb = rb.i64();
+                std::string na = ra.str(), nb = rb.str();
+                return std::tie(va, na) < std::tie(vb, nb) ? b : a;
+              });
+        } catch (const std::exception&) {
+          // the group changed again under us; the next update() sees the new syncId
+          hSyncId_ = 0;
+        }
+        if (gradsOnCuda_) reducer()->poll();  // start the NVLink handle exchange alongside the election
+      }
+    }
+
+    bool haveParams, haveBuffers;
+    {
+      std::lock_guard<std::mutex> nl(netMu_);
+      haveParams = haveNewParameters_;
+      haveBuffers = haveNewBuffers_;
+      netModelVersion_ = modelVersion_;
+      netWaitingForModel_ = isWaitingForModel_;
+    }
+    if (haveParams) {
+      bool ignore;
+      {
+        std::lock_guard<std::mutex> nl(netMu_);
+        ignore = !isWaitingForModel_ && modelVersion_ != newModelVersion_;
+        if (ignore) haveNewParameters_ = false;
+      }
+      if (!ignore) {
+        commitModelUpdate();
+        isWaitingForModel_ = false;
+      }
+    } else if (isWaitingForModel_ && now - isWaitingForModelTimestamp_ >= std::chrono::seconds(60)) {
+      requestModel();
+    } else if (!isWaitingForModel_ && connectedImpl() && syncLeader_ != myName_ &&
+               now - lastReceivedModel_ >= std::chrono::minutes(30)) {
+      lastReceivedModel_ = now;
+      resync();
+    }
+    if (haveBuffers && !haveParams) commitBuffersUpdate();
+    if (!members_.empty()) sendModelUpdates();
+  }
+
+  // ---- misc API --------------------------------------------------------------------------------------------------
+  py::dict getGradientStats() {
+    py::dict r;
+    r["num_gradients"] = stats_.num_gradients;
+    r["num_skipped"] = stats_.num_skipped;
+    r["batch_size"] = stats_.batch_size;
+    return r;
+  }
+  int64_t modelVersion() { return modelVersion_; }
+  void setModelVersion(int64_t v) { modelVersion_ = v; }
+  void setVirtualBatchSize(int n) {
+    std::lock_guard<std::mutex> l(mu_);
+    virtualBatchSize_ = (uint64_t)n;
+  }
+  void setParallelGradients(int n) {
+    if (n < 1 || n > MB_AR_MAX_SLOTS)
+      throw std::runtime_error("set_parallel_gradients: n must be in [1, " + std::to_string(MB_AR_MAX_SLOTS) + "]");
+    std::lock_guard<std::mutex> l(mu_);
+    slots_.clear();
+    slots_.resize(n);
+    nextIndex_ = nextResultIndex_ = 0;
+    reducer_.reset();
+    reducerReady_ = false;
+  }
+  std::string getLeader() {
+    std::lock_guard<std::mutex> l(mu_);
+    return syncLeader_;
+  }
+  bool isLeader() {
+    std::lock_guard<std::mutex> l(mu_);
+    return syncLeader_ == myName_;
+  }
+
+ private:
+  std::mutex mu_;
+  py::object ownGroup_;
+  GroupParts parts_;
+  bool shouldUpdateGroup_ = false;
+  std::string resName_, myName_;
+  std::vector<torch::Tensor> params_, buffers_;
+  bool gradsOnCuda_ = false;
+  int device_ = 0;
+  std::shared_ptr<DeviceReducer> reducer_;
+  bool reducerReady_ = false;
+  std::vector<std::shared_ptr<ReduceSlot>> slots_;
+  size_t nextIndex_ = 0, nextResultIndex_ = 0;
+  uint64_t virtualBatchSize_ = 1;
+  uint32_t hSyncId_ = 0;
+  int64_t modelVersion_ = 0;
+  std::string syncLeader_;
+  std::vector<std::string> members_;
+  bool isFindingLeader_ = false, isWaitingForModel_ = false, hasGradients_ = false, hasReceivedModel_ = false;
+  bool wantsUserState_ = false;
+  std::atomic<bool> hasNewUserState_{false};
+  std::optional<py::object> userState_;
+  mb_ar_hdr stats_{0, 0, 0, 0};
+  std::shared_ptr<SmallReduce> findLeaderOp_;
+  Clock::time_point isWaitingForModelTimestamp_{}, lastReceivedModel_ = Clock::now(), lastSentModel_ = Clock::now(),
+                    lastSentBuffers_ = Clock::now();
+  std::string lastError_;
+  // state touched by the IO thread
+  std::mutex netMu_;
+  uint32_t netSyncId_ = 0;
+  int64_t netModelVersion_ = 0;
+  bool netWaitingForModel_ = false;
+  std::vector<std::string> requestedModelUpdate_;
+  bool haveNewParameters_ = false, haveNewBuffers_ = false;
+  int64_t newModelVersion_ = 0;
+  std::vector<Bytes> newParameters_, newBuffers_;
+  Bytes newUserState_;
+};
+
+void bind_accumulator(py::module_& m) {
+  py::class_<Accumulator>(m, "Accumulator",
+                          "Accumulate and synchronise gradients / model state across the peers of a group "
+                          "(moolib.Accumulator API); CUDA gradients are reduced by the NVLink allreduce kernel.")
+      .def(py::init<std::string, py::object, py::object, py::object>(), py::arg("name"), py::arg("parameters"),
+           py::arg("buffers"), py::arg("group") = py::none())
+      .def("connect", &Accumulator::connect, py::arg("address"))
+      .def("update", &Accumulator::update)
+      .def("connected", &Accumulator::connected)
+      .def("wants_state", &Accumulator::wantsState)
+      .def("has_new_state", &Accumulator::hasNewState)
+      .def("set_state", &Accumulator::setState)
+      .def("state", &Accumulator::state)
+      .def("wants_gradients", &Accumulator::wantsGradients)
+      .def("has_gradients", &Accumulator::hasGradients)
+      .def("reduce_gradients", &Accumulator::reduceGradients, py::arg("batch_size"))
+      .def("skip_gradients", &Accumulator::skipGradients)
+      .def("zero_gradients", &Accumulator::zeroGradients)
+      .def("model_version", &Accumulator::modelVersion)
+      .def("set_model_version", &Accumulator::setModelVersion)
+      .def("set_virtual_batch_size", &Accumulator::setVirtualBatchSize)
+      .def("set_parallel_gradients", &Accumulator::setParallelGradients)
+      .def("get_leader", &Accumulator::getLeader)
+      .def("is_leader", &Accumulator::isLeader)
+      .def("get_gradient_stats", &Accumulator::getGradientStats);
+}
+
+}  // namespace mbh

@@ -40,6 +40,12 @@ inline py::object to_python(const torch::Tensor& t) { return py::reinterpret_ste
 // Number of kernels this process launched through the host layer (bench.py's gpu_launches claim).
 uint64_t& launch_counter();
 
+// CPU tensor <-> bytes (dtype, shape, raw storage): control-plane payloads (late-joiner model sync, CPU-model sums)
+std::string packTensor(const torch::Tensor& t);
+torch::Tensor unpackTensor(const std::string& b);
+std::string pickleDumps(const py::handle& o);
+py::object pickleLoads(const std::string& b);
+
 void bind_batcher(py::module_& m);
 void bind_accumulator(py::module_& m);
 void bind_envpool(py::module_& m);

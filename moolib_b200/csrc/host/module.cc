@@ -6,13 +6,9 @@ PYBIND11_MODULE(_C, m) {
   m.doc() = "moolib_b200 host layer: moolib-compatible Batcher / Accumulator / Group / EnvPool over sm_100a kernels";
   m.attr("__c_abi_version__") = mb_version();
   mbh::bind_batcher(m);
-#ifdef MBH_WITH_ACCUMULATOR
+  mbh::bind_rpc(m);
   mbh::bind_accumulator(m);
-#endif
 #ifdef MBH_WITH_ENVPOOL
   mbh::bind_envpool(m);
-#endif
-#ifdef MBH_WITH_RPC
-  mbh::bind_rpc(m);
 #endif
 }
