@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py -- IMPALA / V-trace learner frames/sec on synthetic 84x84x4 uint8 observations (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1] at N=1, configs[2] at N>1 -- the actor-learner loop of the
+reference's examples/vtrace (examples/impala.py here) with a 256-env synthetic EnvPool x 2 buffers, unroll_length 20
+(T=21), batch_size 32 per learner, virtual_batch_size 32*N, the atari ResNet (1,094,476 fp32 parameters), Adam,
+grad-norm clipping.  One process = one learner = one GPU; a "step" is one optimizer step (640 frames per learner);
+frames/s = unroll_length * batch_size * optimizer_steps / s, the reference's own env_train_steps definition
+(examples/vtrace/experiment.py:155,207-211), summed over all N learners.
+
+Two timed regions of exactly K steps each (after W warm-up steps each), barrier + cuda synchronize on both sides,
+CUDA events, max over ranks:
+  value : observations already resident in HBM, no host reads inside the loop
+  e2e   : observations arrive in pinned host slabs (the EnvPool result format) and are copied H2D every actor step,
+          the grad-norm is read back to the host every optimizer step (as experiment.py:166 does) -- through the
+          public moolib API (Batcher / Accumulator).
+Both go through moolib_b200's Batcher (copy kernels) and Accumulator (stage + NVLink allreduce kernels).
+`roofline` is the batch copy kernel (the dominant moolib_b200 kernel by bytes), timed with CUDA events around every
+Batcher launch inside the `value` region.  Successive launches touch different buffers (T=21 x 256 envs x 28 KB =
+152 MB per time batch, > L2), so inputs are larger than L2 (config.l2 says so).
+
+`--impl reference` runs the UNMODIFIED reference (oracle/_ref, compiled from /root/reference by oracle/build_ref.sh)
+through the same loop on the host cores (device "cpu": its Batcher / Accumulator / RPC allreduce are CPU code and so is
+the model then), bounded in wall time; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "impala_learner_frames_per_sec"
+UNIT = "frames/s"
+ROW_BYTES = 4 * 84 * 84
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=256)
+    ap.add_argument("--max-seconds", type=float, default=150.0, help="wall-time bound of the reference / cpu legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-cuda", type=int, default=1, help="also time the reference built with -DUSE_CUDA (info only)")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class BatchOpTimer:
+    """hooks for examples.impala.LearnerLoop: CUDA events around every Batcher.stack / Batcher.cat in the timed region,
+    on the stream the kernels are launched on (torch's current stream)."""
+
+    def __init__(self, torch, kernel_launches):
+        self.torch, self.kernel_launches = torch, kernel_launches
+        self.enabled = False
+        self.records = []  # (op, start_evt, end_evt, payload_bytes, launches)
+
+    @staticmethod
+    def payload(item):
+        n = 0
+        stack = [item]
+        while stack:
+            x = stack.pop()
+            if isinstance(x, dict):
+                stack.extend(x.values())
+            elif isinstance(x, (list, tuple)):
+                stack.extend(x)
+            elif hasattr(x, "element_size"):
+                n += x.numel() * x.element_size()
+        return n
+
+    def batch_op(self, op, batcher, item):
+        if not self.enabled:
+            getattr(batcher, op)(item)
+            return
+        s, e = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        l0 = self.kernel_launches()
+        s.record()
+        getattr(batcher, op)(item)
+        e.record()
+        self.records.append((op, s, e, self.payload(item), self.kernel_launches() - l0))
+
+    def summary(self, hbm_gbs, peak_kind):
+        by = {}
+        for op, s, e, nbytes, launches in self.records:
+            ms = s.elapsed_time(e)
+            d = by.setdefault(op, {"ms": 0.0, "payload": 0, "launches": 0, "calls": 0})
+            d["ms"] += ms
+            d["payload"] += nbytes
+            d["launches"] += launches
+            d["calls"] += 1
+        out = {}
+        for op, d in by.items():
+            if d["launches"] == 0 or d["ms"] <= 0:
+                continue
+            alg = 2 * d["payload"]  # read every source byte once + write every destination byte once
+            out[op] = {"launches": d["launches"], "avg_launch_us": round(d["ms"] * 1e3 / d["launches"], 3),
+                       "alg_bytes_per_launch": alg // d["launches"], "achieved_gbs": round(alg / d["ms"] / 1e6, 1),
+                       "frac": round(alg / d["ms"] / 1e6 / hbm_gbs, 4)}
+        return out
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, local, world = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("gloo")
+    import moolib_b200 as api
+    from moolib_b200 import _C
+    from examples import impala
+
+    device = f"cuda:{local}"
+    master = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = int(os.environ.get("MASTER_PORT", 29400)) + 23
+    addr = f"{master}:{port}"
+    broker = None
+    if rank == 0:
+        broker = api.Broker()
+        broker.listen(addr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    flags = impala.Flags(actor_batch_size=args.envs, virtual_batch_size=32 * world, device=device)
+    model, optimizer = impala.make_learner(flags)
+    rpc = api.Rpc()
+    rpc.set_name(f"learner{rank}")
+    rpc.connect(addr)
+    group = api.Group(rpc, "impala")
+    group.set_sort_order(rank)
+    acc = api.Accumulator("impala", model.parameters(), model.buffers(), group=group)
+    acc.set_virtual_batch_size(flags.virtual_batch_size)
+
+    hbm, peak_kind = measured_peaks()
+    K, W = args.steps, args.warmup
+    results = {}
+    timer = BatchOpTimer(torch, _C.kernel_launches)
+
+    def wait_for_full_group():
+        # all N learners must be members before the clock starts, otherwise early steps run with a smaller group
+        t0 = time.time()
+        while len(group.members()) != world or not acc.connected():
+            if broker is not None:
+                broker.update()
+            group.update()
+            acc.update()
+            if acc.wants_state():
+                acc.set_state({"optimizer": optimizer.state_dict()})
+            if acc.has_new_state():
+                acc.state()
+            time.sleep(0.001)
+            if time.time() - t0 > 120:
+                raise RuntimeError(f"rank {rank}: group did not form: {group.members()}")
+        barrier()
+
+    wait_for_full_group()
+
+    for mode in ("value", "e2e"):
+        flags.host_obs = mode == "e2e"
+        flags.read_metrics = mode == "e2e"
+        envs = impala.SyntheticEnvPool(flags, device)
+        state = {"t0": None}
+        start_evt, end_evt = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local) if (rank == 0 and mode == "value") else None
+
+        def on_step(res, mode=mode, state=state, start_evt=start_evt, end_evt=end_evt, sampler=sampler):
+            n = res.optimizer_steps
+            if n == W:
+                torch.cuda.synchronize()
+                barrier()
+                if sampler:
+                    sampler.start()
+                state["launch0"] = _C.kernel_launches()
+                state["actor0"] = res.actor_steps
+                timer.enabled = mode == "value"
+                state["t0"] = time.perf_counter()
+                start_evt.record()
+                return True
+            if n == W + K:
+                end_evt.record()
+                torch.cuda.synchronize()
+                state["t1"] = time.perf_counter()
+                state["launches"] = _C.kernel_launches() - state["launch0"]
+                state["actor_steps"] = res.actor_steps - state["actor0"]
+                timer.enabled = False
+                barrier()
+                return False
+            return True
+
+        res = impala.run_learner(api, flags, acc, model, optimizer, envs, on_step, max_seconds=3600, group=group,
+                                 broker=broker, hooks=timer)
+        ms = start_evt.elapsed_time(end_evt)
+        wall = (state["t1"] - state["t0"]) * 1e3
+        t = torch.tensor([ms, wall], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        frames = flags.unroll_length * flags.batch_size * K * world
+        results[mode] = {"ms": t[0].item(), "wall_ms": t[1].item(), "frames": frames,
+                         "value": frames / (t[0].item() / 1e3), "launches": state["launches"],
+                         "actor_steps": state["actor_steps"], "loss": float(res.last_loss),
+                         "h2d": envs.h2d_bytes, "d2h": envs.d2h_bytes}
+        if sampler:
+            results["clocks"] = sampler.stop()
+        # let the peers drain before the next mode
+        for _ in range(50):
+            if broker is not None:
+                broker.update()
+            group.update()
+            acc.update()
+            time.sleep(0.001)
+        barrier()
+
+    if rank == 0:
+        v, e = results["value"], results["e2e"]
+        ops = timer.summary(hbm, peak_kind)
+        dom = ops.get("cat") or ops.get("stack") or {}
+        # H2D per optimizer step: actor steps per optimizer step x one [B] observation slab; D2H: the grad-norm read
+        actor_per_step = e["actor_steps"] / max(K, 1)
+        line = {
+            "metric": METRIC, "value": round(v["value"], 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(v["ms"] / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "IMPALA vtrace learner loop (examples/impala.py), synthetic 84x84x4 u8 obs, "
+                                   f"{args.envs}-env pool x2 buffers, T=21, batch 32/learner, atari ResNet 1,094,476 params"
+                                   + (", 1 learner on 1 B200 (BASELINE configs[1])" if world == 1 else
+                                      f", {world} learner peers, kernel allreduce over NVLink (BASELINE configs[2])"),
+                       "global_batch": 32 * world, "unroll_length": 20, "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2 (152 MB time batches, rotating observation pool)"},
+            "e2e": {"value": round(e["value"], 1), "unit": UNIT, "ms_per_step": round(e["ms"] / K, 4),
+                    "h2d_bytes_per_step": int(actor_per_step * e["h2d"]), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(v["launches"]),
+            "roofline": {"bound": "hbm", "kernel": "copy2d_hybrid_kernel (Batcher.cat: [21,256,..] -> 8 x [21,32,..])",
+                         "achieved": dom.get("achieved_gbs"), "peak": hbm, "unit": "GB/s", "frac": dom.get("frac"),
+                         "traffic": None, "peak_kind": peak_kind, "per_op": ops},
+            "clocks": results.get("clocks"),
+            "wall_ms_per_step": round(v["wall_ms"] / K, 4),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(args)
+            if args.ref_cuda:
+                line["reference_cuda_model"] = reference_cuda_leg(args)
+        print(json.dumps(line), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _run_child(extra_env, argv, timeout):
+    env = dict(os.environ)
+    env.update(extra_env)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + argv, env=env, capture_output=True,
+                           text=True, timeout=timeout)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as ex:  # noqa: BLE001
+        return {"error": repr(ex)[:400]}
+
+
+def cpu_baseline_leg(args):
+    """The reference's own CPU path (oracle/_ref) on this box's host cores, bounded sample of the same workload."""
+    out = _run_child({}, ["--impl", "reference", "--gpus", "1", "--steps", "3", "--warmup", "1", "--max-seconds", "60"],
+                     timeout=400)
+    if "cpu_baseline" in out:
+        return out["cpu_baseline"]
+    return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed",
+            "error": out.get("error")}
+
+
+def reference_cuda_leg(args):
+    """Information only: the reference compiled with -DUSE_CUDA (oracle/_ref_cuda) driving the SAME loop with the model
+    on the GPU -- what a moolib user has today (its Batcher issues per-leaf copy_, its Accumulator stages gradients
+    through pinned host memory and reduces on the CPU)."""
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref_cuda", "moolib")):
+        return {"unavailable": "oracle/_ref_cuda not built"}
+    out = _run_child({"MB_REF_CUDA": "1"}, ["--impl", "reference", "--gpus", "1", "--steps", str(args.steps),
+                                            "--warmup", str(args.warmup), "--max-seconds", "90"], timeout=500)
+    return {k: out.get(k) for k in ("value", "unit", "ms_per_step", "e2e", "steps", "error") if k in out}
+
+
+def run_reference(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    use_cuda = os.environ.get("MB_REF_CUDA") == "1"
+    ref_dir = os.path.join(ROOT, "oracle", "_ref_cuda" if use_cuda else "_ref")
+    import torch
+    sys.path.insert(0, ref_dir)
+    try:
+        import moolib as ref
+    except Exception as ex:  # the oracle always exists in this repo; say so loudly if the build is missing
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {ex!r}"[:200]}))
+        return
+    from examples import impala
+
+    n_peers = max(world, args.gpus) if not use_cuda else 1
+    device = "cuda:0" if use_cuda else "cpu"
+    cores = os.cpu_count()
+    torch.set_num_threads(max(1, cores // n_peers))
+    K, W = args.steps, args.warmup
+    port = 29400 + 57 + (os.getpid() % 500)
+    addr = f"127.0.0.1:{port}"
+    broker = ref.Broker()
+    broker.listen(addr)
+    loops = []
+    for i in range(n_peers):
+        flags = impala.Flags(actor_batch_size=args.envs, virtual_batch_size=32 * n_peers, device=device,
+                             host_obs=True, read_metrics=True)
+        flags.seed += i
+        model, opt = impala.make_learner(flags)
+        acc = ref.Accumulator("impala", model.parameters(), model.buffers())
+        acc.set_virtual_batch_size(flags.virtual_batch_size)
+        acc.connect(addr)
+        envs = impala.SyntheticEnvPool(flags, device)
+        loops.append(impala.LearnerLoop(ref, flags, acc, model, opt, envs, broker=broker if i == 0 else None))
+
+    def sync():
+        if use_cuda:
+            torch.cuda.synchronize()
+
+    t_begin = time.time()
+    t0 = None
+    done_steps = 0
+    while True:
+        for lp in loops:
+            lp.tick()
+        n = min(lp.res.optimizer_steps for lp in loops)
+        if t0 is None and n >= W:
+            sync()
+            t0 = time.perf_counter()
+            base = [lp.res.optimizer_steps for lp in loops]
+        if t0 is not None:
+            done_steps = min(lp.res.optimizer_steps - b for lp, b in zip(loops, base))
+            if done_steps >= K or time.time() - t_begin > args.max_seconds:
+                break
+        elif time.time() - t_begin > args.max_seconds:
+            break
+    sync()
+    if t0 is None or done_steps == 0:
+        print(json.dumps({"impl": "reference", "unavailable": "no timed step completed within --max-seconds"}))
+        return
+    dt = time.perf_counter() - t0
+    total_steps = sum(lp.res.optimizer_steps - b for lp, b in zip(loops, base))
+    frames = 20 * 32 * total_steps
+    value = frames / dt
+    sample = (f"{done_steps} of {K} optimizer steps per peer x {n_peers} peer(s) in one process, device={device}, "
+              f"full config (256 envs, T=21, batch 32), {dt:.1f} s")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": done_steps, "warmup": W, "ms_per_step": round(dt * 1e3 / max(done_steps, 1), 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "IMPALA vtrace learner loop (examples/impala.py) driven through the UNMODIFIED "
+                                   f"reference moolib ({'oracle/_ref_cuda, model on cuda:0' if use_cuda else 'oracle/_ref, host cores'})",
+                       "global_batch": 32 * n_peers, "parallelism": f"dp{n_peers}"},
+            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": sample},
+            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    os._exit(0)  # the reference's RPC threads do not always join cleanly at interpreter exit
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -215,46 +215,56 @@ struct Batcher {
     }
   }
 
-  // reference: src/moolib.cc:767-811
+  // reference: src/moolib.cc:767-811.  Same carry loop; the copies of ALL batches this item completes (plus the
+  // partial one it starts) go out as ONE launch, and the finished batches are handed over only after that launch is
+  // enqueued, so a consumer can never get ahead of the copy on the stream.
   template <typename Callback>
   void cat(py::object value, Callback&& callback) {
     int64_t localInputOffset = 0;
-    while (true) {
+    std::vector<py::object> finished;
+    std::exception_ptr error;
+    {
       std::unique_lock<std::mutex> l(batchMutex);
-      catBatchInputOffset = localInputOffset;
-      catBatchInputSize = 0;
-      if (!target) {
-        catBatchOutputOffset = 0;
-        nTensors = 0;
-        target = prepareForBatchCopy<true>(value);
-        isDoingCat = true;
-      } else {
-        if (!isDoingCat) {
-          throw std::runtime_error(
-              "Batcher.cat: Previously called with stack; cannot mix cat/stack within the same batch");
+      try {
+      while (true) {
+        catBatchInputOffset = localInputOffset;
+        catBatchInputSize = 0;
+        if (!target) {
+          catBatchOutputOffset = 0;
+          nTensors = 0;
+          target = prepareForBatchCopy<true>(value);
+          isDoingCat = true;
+        } else {
+          if (!isDoingCat) {
+            throw std::runtime_error(
+                "Batcher.cat: Previously called with stack; cannot mix cat/stack within the same batch");
+          }
+          currentTensor = 0;
+          visit<true>(*target, value);
+          if (currentTensor != nTensors) {
+            throw std::runtime_error("num tensors mismatch in batch operation; got " + std::to_string(currentTensor) +
+                                     " tensors, batch has " + std::to_string(nTensors));
+          }
         }
-        currentTensor = 0;
-        visit<true>(*target, value);
-        if (currentTensor != nTensors) {
-          throw std::runtime_error("num tensors mismatch in batch operation; got " + std::to_string(currentTensor) +
-                                   " tensors, batch has " + std::to_string(nTensors));
+        int64_t inputSize = catBatchInputSize - localInputOffset;
+        int64_t left = batchSize - catBatchOutputOffset;
+        if (inputSize >= left) {
+          finished.push_back(std::move(*target));
+          target.reset();
+          if (inputSize == left) break;
+          localInputOffset += left;
+        } else {
+          catBatchOutputOffset += inputSize;
+          break;
         }
+      }
+      } catch (...) {
+        error = std::current_exception();  // the copies already described are still issued, as the reference's were
       }
       copies.launch();
-      int64_t inputSize = catBatchInputSize - localInputOffset;
-      int64_t left = batchSize - catBatchOutputOffset;
-      if (inputSize >= left) {
-        py::object r = std::move(*target);
-        target.reset();
-        l.unlock();
-        callback(std::move(r));
-        if (inputSize == left) break;
-        localInputOffset += left;
-      } else {
-        catBatchOutputOffset += inputSize;
-        break;
-      }
     }
+    for (auto& r : finished) callback(std::move(r));
+    if (error) std::rethrow_exception(error);
   }
 
   // reference: src/moolib.cc:813-845
@@ -262,7 +272,12 @@ struct Batcher {
     std::lock_guard<std::mutex> l(batchMutex);
     if (!target) {
       nTensors = 0;
-      target = prepareForBatchCopy<false>(value);
+      try {
+        target = prepareForBatchCopy<false>(value);
+      } catch (...) {
+        copies.launch();
+        throw;
+      }
       nextStackIndex = 1;
       isDoingCat = false;
     } else {
@@ -271,8 +286,14 @@ struct Batcher {
             "Batcher.stack: Previously called with cat; cannot mix cat/stack within the same batch");
       }
       currentTensor = 0;
-      visit<false>(*target, value);
+      try {
+        visit<false>(*target, value);
+      } catch (...) {
+        copies.launch();
+        throw;
+      }
       if (currentTensor != nTensors) {
+        copies.launch();
         throw std::runtime_error("num tensors mismatch in batch operation; got " + std::to_string(currentTensor) +
                                  " tensors, batch has " + std::to_string(nTensors));
       }

@@ -1,0 +1,150 @@
+"""moolib_b200.Accumulator / Group.all_reduce with CUDA tensors: the C++ host layer drives the stage + NVLink allreduce
+kernels.  One GPU: single-member group (N=1 short-circuit, src/group.h:738-741, still through the kernels).
+Several GPUs: one process per GPU under torchrun, CUDA IPC handles exchanged over the Group's own control plane."""
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import pytest
+import torch
+
+import moolib_b200 as moolib
+import oracle
+from helpers import gen_input
+from moolib_b200 import _C
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NGPU = torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def test_single_learner_accumulator_on_gpu():
+    addr = "127.0.0.1:47301"
+    broker = moolib.Broker()
+    broker.listen(addr)
+    m = torch.nn.Linear(32, 31).cuda()
+    acc = moolib.Accumulator("acc", m.parameters(), m.buffers())
+    acc.set_virtual_batch_size(20)
+    acc.connect(addr)
+    t0 = time.time()
+    while not acc.connected():
+        broker.update()
+        acc.update()
+        assert time.time() - t0 < 60
+    assert acc.is_leader()
+    before = _C.kernel_launches()
+    gw1, gb1 = gen_input(1, [31, 32], "f32"), gen_input(2, [31], "f32")
+    gw2, gb2 = gen_input(3, [31, 32], "f32"), gen_input(4, [31], "f32")
+    for gw, gb in ((gw1, gb1), (gw2, gb2)):  # two local contributions before the gate (20) opens
+        while not acc.wants_gradients():
+            broker.update()
+            acc.update()
+        m.weight.grad = torch.from_numpy(gw.copy()).cuda()
+        m.bias.grad = torch.from_numpy(gb.copy()).cuda()
+        acc.reduce_gradients(10)
+        assert not m.weight.grad.any().item()  # zeroed by the stage kernel
+        for _ in range(20):
+            broker.update()
+            acc.update()
+    t0 = time.time()
+    while not acc.has_gradients():
+        broker.update()
+        acc.update()
+        assert time.time() - t0 < 30
+    assert _C.kernel_launches() - before == 3  # stage, stage(+=), allreduce
+    st = np.zeros(oracle.flat_layout([992, 31])[1], dtype=np.float32)
+    oracle.stage(st, [gw1.reshape(-1).copy(), gb1.copy()])
+    oracle.stage(st, [gw2.reshape(-1).copy(), gb2.copy()], accumulate=True)
+    exact, eh = oracle.allreduce_rankorder([st], [(2, 0, 20)])
+    assert m.weight.grad.cpu().numpy().reshape(-1).tobytes() == exact[:992].tobytes()
+    assert m.bias.grad.cpu().numpy().tobytes() == exact[992:992 + 31].tobytes()
+    assert acc.get_gradient_stats() == {"num_gradients": 2, "num_skipped": 0, "batch_size": 20}
+    assert acc.model_version() == 1
+    acc.zero_gradients()
+    assert not acc.has_gradients() and not m.weight.grad.any().item()
+
+
+WORKER = r"""
+import os, sys, time, numpy as np, torch
+sys.path.insert(0, os.environ['MB_ROOT']); sys.path.insert(0, os.path.join(os.environ['MB_ROOT'], 'tests'))
+import oracle, moolib_b200 as moolib
+from helpers import gen_input
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+addr = '127.0.0.1:' + os.environ['MB_PORT']
+broker = None
+if rank == 0:
+    broker = moolib.Broker(); broker.listen(addr)
+rpc = moolib.Rpc(); rpc.set_name(f'peer{rank}'); rpc.set_timeout(30); rpc.connect(addr)
+group = moolib.Group(rpc, 'g'); group.set_sort_order(rank)
+torch.manual_seed(0)
+m = torch.nn.Linear(32, 31).cuda()
+acc = moolib.Accumulator('acc', m.parameters(), m.buffers(), group=group)
+acc.set_virtual_batch_size(10 * world)
+def pump():
+    if broker: broker.update()
+    group.update(); acc.update()
+    if acc.wants_state(): acc.set_state({'k': 1})
+    if acc.has_new_state(): acc.state()
+t0 = time.time()
+while not (acc.connected() and len(group.members()) == world):
+    pump(); time.sleep(0.001); assert time.time() - t0 < 90, group.members()
+# group.all_reduce on CUDA tensors (A8)
+x = torch.from_numpy(gen_input(900 + rank, [64, 64], 'f32')).cuda()
+f = group.all_reduce('t', x)
+t0 = time.time()
+while not f.done():
+    pump(); assert time.time() - t0 < 60
+r = f.result()
+exact, _ = oracle.allreduce_rankorder([gen_input(900 + q, [64 * 64], 'f32') for q in range(world)], [(1, 0, 1)] * world, scale=False)
+assert r.data_ptr() == x.data_ptr() and x.cpu().numpy().reshape(-1).tobytes() == exact.tobytes()
+# Accumulator rounds
+numels = [992, 31]
+offs, total = oracle.flat_layout(numels)
+for rnd in range(5):
+    t0 = time.time()
+    while not acc.wants_gradients():
+        pump(); assert time.time() - t0 < 60
+    skip = (rnd == 3 and rank == world - 1)
+    if skip:
+        acc.skip_gradients()
+    else:
+        m.weight.grad = torch.from_numpy(gen_input(100 * rnd + 2 * rank, [31, 32], 'f32')).cuda()
+        m.bias.grad = torch.from_numpy(gen_input(100 * rnd + 2 * rank + 1, [31], 'f32')).cuda()
+        acc.reduce_gradients(10)
+    acc.set_virtual_batch_size(10 * (world - 1) if rnd == 3 else 10 * world)
+    t0 = time.time()
+    while not acc.has_gradients():
+        pump(); assert time.time() - t0 < 60, f'round {rnd}'
+    ins, hdrs = [], []
+    for q in range(world):
+        if rnd == 3 and q == world - 1:
+            ins.append(None); hdrs.append((0, 1, 0)); continue
+        f_ = np.zeros(total, dtype=np.float32)
+        f_[:992] = gen_input(100 * rnd + 2 * q, [992], 'f32'); f_[992:992 + 31] = gen_input(100 * rnd + 2 * q + 1, [31], 'f32')
+        ins.append(f_); hdrs.append((1, 0, 10))
+    exact, eh = oracle.allreduce_rankorder(ins, hdrs, numel=total)
+    assert m.weight.grad.cpu().numpy().reshape(-1).tobytes() == exact[:992].tobytes(), f'rank {rank} round {rnd}'
+    assert m.bias.grad.cpu().numpy().tobytes() == exact[992:1023].tobytes()
+    s = acc.get_gradient_stats()
+    assert (s['num_gradients'], s['num_skipped'], s['batch_size']) == eh[:3], (s, eh)
+    acc.zero_gradients()
+for _ in range(200):
+    pump(); time.sleep(0.001)
+print(f'rank {rank} OK', flush=True)
+os._exit(0)
+"""
+
+
+@pytest.mark.parametrize("world", [n for n in (2, 4, 8) if n <= NGPU])
+def test_accumulator_across_processes(world, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MB_ROOT=ROOT, MB_PORT=str(47400 + world))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("OK") == world
