@@ -182,9 +182,16 @@ def run_ours(args):
         broker = api.Broker()
         broker.listen(addr)
 
+    service = {"fn": lambda: None}
+
     def barrier():
+        # Peers may still need this rank's control plane while it waits (e.g. the elected leader serving the model to
+        # a late joiner), so keep servicing it instead of blocking inside gloo.
         if world > 1:
-            dist.barrier()
+            w = dist.barrier(async_op=True)
+            while not w.is_completed():
+                service["fn"]()
+                time.sleep(0.0002)
 
     flags = impala.Flags(actor_batch_size=args.envs, virtual_batch_size=32 * world, device=device)
     model, optimizer = impala.make_learner(flags)
@@ -196,6 +203,17 @@ def run_ours(args):
     acc = api.Accumulator("impala", model.parameters(), model.buffers(), group=group)
     acc.set_virtual_batch_size(flags.virtual_batch_size)
 
+    def pump():
+        if broker is not None:
+            broker.update()
+        group.update()
+        acc.update()
+        if acc.wants_state():
+            acc.set_state({"optimizer": optimizer.state_dict()})
+        if acc.has_new_state():
+            acc.state()
+
+    service["fn"] = pump
     hbm, peak_kind = measured_peaks()
     K, W = args.steps, args.warmup
     results = {}
@@ -205,14 +223,7 @@ def run_ours(args):
         # all N learners must be members before the clock starts, otherwise early steps run with a smaller group
         t0 = time.time()
         while len(group.members()) != world or not acc.connected():
-            if broker is not None:
-                broker.update()
-            group.update()
-            acc.update()
-            if acc.wants_state():
-                acc.set_state({"optimizer": optimizer.state_dict()})
-            if acc.has_new_state():
-                acc.state()
+            pump()
             time.sleep(0.001)
             if time.time() - t0 > 120:
                 raise RuntimeError(f"rank {rank}: group did not form: {group.members()}")
@@ -268,10 +279,7 @@ def run_ours(args):
             results["clocks"] = sampler.stop()
         # let the peers drain before the next mode
         for _ in range(50):
-            if broker is not None:
-                broker.update()
-            group.update()
-            acc.update()
+            pump()
             time.sleep(0.001)
         barrier()
 
@@ -328,12 +336,12 @@ def _run_child(extra_env, argv, timeout):
 
 def cpu_baseline_leg(args):
     """The reference's own CPU path (oracle/_ref) on this box's host cores, bounded sample of the same workload."""
-    out = _run_child({}, ["--impl", "reference", "--gpus", "1", "--steps", "3", "--warmup", "1", "--max-seconds", "60"],
-                     timeout=400)
+    out = _run_child({}, ["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "0", "--max-seconds", "150"],
+                     timeout=600)
     if "cpu_baseline" in out:
         return out["cpu_baseline"]
     return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed",
-            "error": out.get("error")}
+            "error": out.get("error") or out.get("unavailable") or str(out)[:300]}
 
 
 def reference_cuda_leg(args):

@@ -50,18 +50,22 @@ struct HostResult {
   uint32_t epoch;
 };
 
+// One rank's symmetric memory is ONE cudaMalloc block whose size is a multiple of 2 MiB: [staging | SyncBlock].  CUDA IPC
+// shares whole 2 MiB-granular blocks and cudaIpcOpenMemHandle returns the BASE of the block a pointer lives in, so a
+// small allocation that the driver sub-allocated next to others would be opened at the wrong address; owning whole
+// blocks (and carrying the offset from the block base, measured with cuMemGetAddressRange) rules that out.
 struct HandleImpl {
   uint32_t magic;
   int32_t pid;
   int32_t device;
   int32_t rank;
-  uint64_t staging_ptr;
-  uint64_t sync_ptr;
+  uint64_t block_ptr;     // owner's virtual address of the block (same-process peers use it directly)
+  uint64_t base_offset;   // block_ptr - base of the driver allocation that the IPC handle maps
+  uint64_t sync_offset;   // SyncBlock offset inside the block
   uint64_t max_bytes;
   int32_t nslots;
   int32_t ipc_ok;
-  cudaIpcMemHandle_t h_staging;
-  cudaIpcMemHandle_t h_sync;
+  cudaIpcMemHandle_t h_block;
 };
 static_assert(sizeof(HandleImpl) <= MB_AR_HANDLE_BYTES, "mb_ar_handle too small");
 
@@ -84,8 +88,11 @@ struct DeviceGuard {
 struct mb_ar_ctx {
   int rank = 0, world = 1, device = 0, nslots = 1;
   uint64_t max_bytes = 0;  // per staging buffer, multiple of 16
+  void* block = nullptr;             // the one IPC-exported allocation: [staging | SyncBlock], multiple of 2 MiB
+  uint64_t block_bytes = 0, sync_offset = 0;
   float* staging = nullptr;          // nslots * 2 buffers (parity double-buffering, see mb_ar_allreduce)
   mb::SyncBlock* sync = nullptr;
+  void* peer_block[MB_AR_MAX_WORLD] = {};  // IPC-opened base of each peer's block (what must be closed)
   float* peer_staging[MB_AR_MAX_WORLD] = {};
   mb::SyncBlock* peer_sync[MB_AR_MAX_WORLD] = {};
   bool imported[MB_AR_MAX_WORLD] = {};
@@ -377,17 +384,23 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_oneshot_kernel(const __grid_
   const float s = reduce_scale(p, tot);
   constexpr int U = Unroll<NR>::value;
   const uint64_t stride = (uint64_t)gridDim.x * kArThreads;
-  for (uint64_t v0 = (uint64_t)blockIdx.x * kArThreads + threadIdx.x; v0 < p.total_vec; v0 += stride * U) {
+  uint64_t v0 = (uint64_t)blockIdx.x * kArThreads + threadIdx.x;
+  // full groups of U vectors per thread (all U*NR loads in flight), then the tail one vector at a time.  (Out-of-range
+  // lanes must NOT be clamped to a common address: thousands of threads loading one peer line serialise on NVLink.)
+  for (; v0 + (uint64_t)(U - 1) * stride < p.total_vec; v0 += stride * U) {
     uint64_t v[U];
     float4 r[U];
 #pragma unroll
-    for (int k = 0; k < U; ++k) v[k] = min(v0 + (uint64_t)k * stride, p.total_vec - 1);  // clamped, stores predicated
+    for (int k = 0; k < U; ++k) v[k] = v0 + (uint64_t)k * stride;
     reduce_vecs<NR, U>(p.stage, mask, v, r);  // mask == 0 -> zeros (src/accumulator.cc:426-428)
 #pragma unroll
-    for (int k = 0; k < U; ++k) {
-      if (v0 + (uint64_t)k * stride < p.total_vec)
-        scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], scale_vec(r[k], s, do_scale));
-    }
+    for (int k = 0; k < U; ++k) scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], scale_vec(r[k], s, do_scale));
+  }
+  for (; v0 < p.total_vec; v0 += stride) {
+    uint64_t v[1] = {v0};
+    float4 r[1];
+    reduce_vecs<NR, 1>(p.stage, mask, v, r);
+    scatter_vec(p.dst_tab, s_off, p.ntensors, v0, scale_vec(r[0], s, do_scale));
   }
   write_result(p, tot);
 }
@@ -418,21 +431,28 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_
     constexpr int U = Unroll<NR>::value;
     const uint64_t base = (uint64_t)p.rank * p.slice_vec;
     const uint64_t end = min(p.total_vec, base + p.slice_vec);  // my slice is [base, end)
-    for (uint64_t v0 = base + j0; v0 < end; v0 += stride * U) {
+    auto emit = [&](uint64_t v, const float4& red) {
+      const float4 o = scale_vec(red, s, do_scale);
+#pragma unroll
+      for (int q = 0; q < NR; ++q)
+        if (q != p.rank) st_f4(p.stage[q] + v * 4, o);
+      scatter_vec(p.dst_tab, s_off, p.ntensors, v, o);
+    };
+    uint64_t v0 = base + j0;
+    for (; v0 + (uint64_t)(U - 1) * stride < end; v0 += stride * U) {
       uint64_t v[U];
       float4 r[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) v[k] = min(v0 + (uint64_t)k * stride, end - 1);
+      for (int k = 0; k < U; ++k) v[k] = v0 + (uint64_t)k * stride;
       reduce_vecs<NR, U>(p.stage, mask, v, r);
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        if (v0 + (uint64_t)k * stride >= end) continue;
-        const float4 o = scale_vec(r[k], s, do_scale);
-#pragma unroll
-        for (int q = 0; q < NR; ++q)
-          if (q != p.rank) st_f4(p.stage[q] + v[k] * 4, o);
-        scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], o);
-      }
+      for (int k = 0; k < U; ++k) emit(v[k], r[k]);
+    }
+    for (; v0 < end; v0 += stride) {
+      uint64_t v[1] = {v0};
+      float4 r[1];
+      reduce_vecs<NR, 1>(p.stage, mask, v, r);
+      emit(v0, r[0]);
     }
   }
   if (!block_barrier(p, true)) {
@@ -564,11 +584,13 @@ int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int ns
     cudaError_t e__ = (expr);                                                         \
     if (e__ != cudaSuccess) return fail(cuda_fail(e__, #expr, __FILE__, __LINE__));   \
   } while (0)
-  const uint64_t staging_bytes = ctx->max_bytes * 2 * (uint64_t)nslots;
-  MB_TRY(cudaMalloc(&ctx->staging, staging_bytes));
-  MB_TRY(cudaMemset(ctx->staging, 0, staging_bytes));
-  MB_TRY(cudaMalloc(&ctx->sync, sizeof(SyncBlock)));
-  MB_TRY(cudaMemset(ctx->sync, 0, sizeof(SyncBlock)));
+  const uint64_t staging_bytes = (ctx->max_bytes * 2 * (uint64_t)nslots + 255) & ~255ull;
+  ctx->sync_offset = staging_bytes;
+  ctx->block_bytes = (staging_bytes + sizeof(SyncBlock) + (2ull << 20) - 1) & ~((2ull << 20) - 1);
+  MB_TRY(cudaMalloc(&ctx->block, ctx->block_bytes));
+  MB_TRY(cudaMemset(ctx->block, 0, ctx->block_bytes));
+  ctx->staging = static_cast<float*>(ctx->block);
+  ctx->sync = reinterpret_cast<SyncBlock*>(static_cast<char*>(ctx->block) + ctx->sync_offset);
   MB_TRY(cudaHostAlloc(&ctx->result_host, sizeof(HostResult) * MB_AR_MAX_SLOTS, cudaHostAllocMapped));
   std::memset(ctx->result_host, 0, sizeof(HostResult) * MB_AR_MAX_SLOTS);
   MB_TRY(cudaHostGetDevicePointer(&ctx->result_dev, ctx->result_host, 0));
@@ -587,12 +609,10 @@ int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int ns
 
 static void close_peers(mb_ar_ctx* ctx) {
   for (int r = 0; r < MB_AR_MAX_WORLD; ++r) {
-    if (ctx->ipc_opened[r]) {
-      if (ctx->peer_staging[r]) cudaIpcCloseMemHandle(ctx->peer_staging[r]);
-      if (ctx->peer_sync[r]) cudaIpcCloseMemHandle(ctx->peer_sync[r]);
-    }
+    if (ctx->ipc_opened[r] && ctx->peer_block[r]) cudaIpcCloseMemHandle(ctx->peer_block[r]);
     ctx->ipc_opened[r] = false;
     ctx->imported[r] = false;
+    ctx->peer_block[r] = nullptr;
     ctx->peer_staging[r] = nullptr;
     ctx->peer_sync[r] = nullptr;
   }
@@ -606,8 +626,7 @@ int mb_ar_ctx_destroy(mb_ar_ctx* ctx) {
   ctx->peer_staging[ctx->rank] = nullptr;
   ctx->peer_sync[ctx->rank] = nullptr;
   close_peers(ctx);
-  if (ctx->staging) cudaFree(ctx->staging);
-  if (ctx->sync) cudaFree(ctx->sync);
+  if (ctx->block) cudaFree(ctx->block);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
   if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
   for (int w = 0; w < 2; ++w)
@@ -626,13 +645,27 @@ int mb_ar_ctx_export(mb_ar_ctx* ctx, mb_ar_handle* out) {
   h.pid = (int32_t)getpid();
   h.device = ctx->device;
   h.rank = ctx->rank;
-  h.staging_ptr = reinterpret_cast<uint64_t>(ctx->staging);
-  h.sync_ptr = reinterpret_cast<uint64_t>(ctx->sync);
+  h.block_ptr = reinterpret_cast<uint64_t>(ctx->block);
+  h.sync_offset = ctx->sync_offset;
   h.max_bytes = ctx->max_bytes;
   h.nslots = ctx->nslots;
   h.ipc_ok = 1;
-  if (cudaIpcGetMemHandle(&h.h_staging, ctx->staging) != cudaSuccess ||
-      cudaIpcGetMemHandle(&h.h_sync, ctx->sync) != cudaSuccess) {
+  h.base_offset = 0;
+  {
+    // offset of our block inside the driver allocation the IPC handle maps (0 for a block-owning allocation)
+    typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
+      unsigned long long base = 0;
+      size_t size = 0;
+      if (reinterpret_cast<GetRangeFn>(fn)(&base, &size, (unsigned long long)h.block_ptr) == 0 && base)
+        h.base_offset = h.block_ptr - base;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  if (cudaIpcGetMemHandle(&h.h_block, ctx->block) != cudaSuccess) {
     cudaGetLastError();  // same-process peers can still import by pointer
     h.ipc_ok = 0;
   }
@@ -654,10 +687,8 @@ int mb_ar_ctx_import(mb_ar_ctx* ctx, int peer_rank, const mb_ar_handle* handle) 
   if (peer_rank == ctx->rank) return MB_OK;
   DeviceGuard g(ctx->device);
   if (ctx->imported[peer_rank]) {
-    if (ctx->ipc_opened[peer_rank]) {
-      cudaIpcCloseMemHandle(ctx->peer_staging[peer_rank]);
-      cudaIpcCloseMemHandle(ctx->peer_sync[peer_rank]);
-    }
+    if (ctx->ipc_opened[peer_rank] && ctx->peer_block[peer_rank]) cudaIpcCloseMemHandle(ctx->peer_block[peer_rank]);
+    ctx->peer_block[peer_rank] = nullptr;
     ctx->imported[peer_rank] = ctx->ipc_opened[peer_rank] = false;
   }
   if (h.pid == (int32_t)getpid()) {
@@ -672,24 +703,20 @@ int mb_ar_ctx_import(mb_ar_ctx* ctx, int peer_rank, const mb_ar_handle* handle) 
       if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
       else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
     }
-    ctx->peer_staging[peer_rank] = reinterpret_cast<float*>(h.staging_ptr);
-    ctx->peer_sync[peer_rank] = reinterpret_cast<SyncBlock*>(h.sync_ptr);
+    ctx->peer_staging[peer_rank] = reinterpret_cast<float*>(h.block_ptr);
+    ctx->peer_sync[peer_rank] = reinterpret_cast<SyncBlock*>(h.block_ptr + h.sync_offset);
     ctx->ipc_opened[peer_rank] = false;
   } else {
     if (!h.ipc_ok) {
       set_error("mb_ar_ctx_import: peer %d could not export CUDA IPC handles", peer_rank);
       return MB_ESTATE;
     }
-    void* ps = nullptr;
-    void* py = nullptr;
-    MB_CUDA(cudaIpcOpenMemHandle(&ps, h.h_staging, cudaIpcMemLazyEnablePeerAccess));
-    cudaError_t e = cudaIpcOpenMemHandle(&py, h.h_sync, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      cudaIpcCloseMemHandle(ps);
-      return cuda_fail(e, "cudaIpcOpenMemHandle(sync)", __FILE__, __LINE__);
-    }
-    ctx->peer_staging[peer_rank] = static_cast<float*>(ps);
-    ctx->peer_sync[peer_rank] = static_cast<SyncBlock*>(py);
+    void* base = nullptr;
+    MB_CUDA(cudaIpcOpenMemHandle(&base, h.h_block, cudaIpcMemLazyEnablePeerAccess));
+    char* blk = static_cast<char*>(base) + h.base_offset;
+    ctx->peer_block[peer_rank] = base;
+    ctx->peer_staging[peer_rank] = reinterpret_cast<float*>(blk);
+    ctx->peer_sync[peer_rank] = reinterpret_cast<SyncBlock*>(blk + h.sync_offset);
     ctx->ipc_opened[peer_rank] = true;
   }
   ctx->imported[peer_rank] = true;

@@ -22,7 +22,14 @@ torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
 dist.init_process_group('gloo')
 numels = [992, 31, 5, 300001]
 total = _lib.flat_numel(numels)
+# a small context first: its 64 KiB sync block must not end up sub-allocated next to the next context's (CUDA IPC maps
+# whole 2 MiB blocks -- regression test for handles that were opened at the wrong offset)
+small = peer.make_context(4096, nslots=1)
 ctx = peer.make_context(total * 4, nslots=2)
+one = torch.full((8,), float(rank + 1), device='cuda')
+small.stage([one]); out8 = torch.empty(8, device='cuda'); small.allreduce_flat(out8)
+torch.cuda.synchronize()
+assert (out8 == world * (world + 1) / 2).all().item() and small.result()[1] == 0
 offs, _ = oracle.flat_layout(numels)
 for rnd in range(6):
     algo = [_lib.MB_AR_ALGO_ONESHOT, _lib.MB_AR_ALGO_TWOSHOT][rnd % 2]
@@ -46,6 +53,7 @@ for rnd in range(6):
     assert got.tobytes() == exact.tobytes(), f'rank {rank} round {rnd}'
     assert ctx.result(rnd % 2) == (eh, 0)
 dist.barrier()
+small.close()
 ctx.close()
 print(f'rank {rank} OK')
 """
