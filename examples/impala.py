@@ -113,6 +113,7 @@ class Flags:
     host_obs: bool = True             # True: observations come from pinned host slabs (EnvPool format), H2D per step
     read_metrics: bool = True         # True: grad-norm .item() per optimizer step, as experiment.py:166 does
     obs_pool: int = 8                 # distinct pre-generated observation slabs per buffer (defeats caching)
+    max_queued_batches: int = 64      # back-pressure on the actor side (64 x 19 MB)
     seed: int = 1234
 
 
@@ -253,6 +254,11 @@ class LearnerLoop:
             return False
         if acc.wants_gradients():
             acc.skip_gradients()
+        if self.learn_batcher.size() >= self.flags.max_queued_batches:
+            # (not in the reference loop) never let unconsumed learner batches pile up in device memory while the
+            # accumulator is not asking for gradients
+            time.sleep(0.0002)
+            return False
         cur = self.next_env_index
         self.next_env_index = (self.next_env_index + 1) % flags.num_actor_batches
         es = self.env_states[cur]

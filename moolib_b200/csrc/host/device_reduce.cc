@@ -151,9 +151,11 @@ bool DeviceReducer::poll() {
 // ---- DeviceReducerSet ----------------------------------------------------------------------------------------------
 std::shared_ptr<DeviceReducer> DeviceReducerSet::get(const std::string& tag, int device, uint64_t maxBytes, int nslots) {
   std::lock_guard<std::mutex> l(mu_);
-  std::string key = tag + "/" + std::to_string(device) + "/" + std::to_string(maxBytes) + "/" + std::to_string(nslots);
+  // the exchange name must be identical on every rank, so it must NOT contain the local device index
+  std::string name = tag + "/" + std::to_string(maxBytes) + "/" + std::to_string(nslots);
+  std::string key = name + "@" + std::to_string(device);
   auto& r = reducers_[key];
-  if (!r) r = std::make_shared<DeviceReducer>(service_, info_, key, device, maxBytes, nslots);
+  if (!r) r = std::make_shared<DeviceReducer>(service_, info_, name, device, maxBytes, nslots);
   return r;
 }
 

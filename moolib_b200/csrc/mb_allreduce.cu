@@ -382,25 +382,28 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_oneshot_kernel(const __grid_
   const mb_ar_hdr tot = s_total;
   const bool do_scale = p.scale && tot.num_gradients != 0;
   const float s = reduce_scale(p, tot);
+  // Each block-iteration owns a contiguous chunk of U*512 vectors (U*8 KiB): thread t handles chunk[k*512 + t],
+  // k < U, all U*NR peer loads in flight before the first add.  (Lanes must never be clamped to a common address:
+  // thousands of threads loading one peer line serialise on NVLink -- measured 10x slowdowns.)
   constexpr int U = Unroll<NR>::value;
-  const uint64_t stride = (uint64_t)gridDim.x * kArThreads;
-  uint64_t v0 = (uint64_t)blockIdx.x * kArThreads + threadIdx.x;
-  // full groups of U vectors per thread (all U*NR loads in flight), then the tail one vector at a time.  (Out-of-range
-  // lanes must NOT be clamped to a common address: thousands of threads loading one peer line serialise on NVLink.)
-  for (; v0 + (uint64_t)(U - 1) * stride < p.total_vec; v0 += stride * U) {
-    uint64_t v[U];
-    float4 r[U];
+  constexpr uint64_t kChunk = (uint64_t)U * kArThreads;
+  for (uint64_t base = (uint64_t)blockIdx.x * kChunk; base < p.total_vec; base += (uint64_t)gridDim.x * kChunk) {
+    if (base + kChunk <= p.total_vec) {
+      uint64_t v[U];
+      float4 r[U];
 #pragma unroll
-    for (int k = 0; k < U; ++k) v[k] = v0 + (uint64_t)k * stride;
-    reduce_vecs<NR, U>(p.stage, mask, v, r);  // mask == 0 -> zeros (src/accumulator.cc:426-428)
+      for (int k = 0; k < U; ++k) v[k] = base + (uint64_t)k * kArThreads + threadIdx.x;
+      reduce_vecs<NR, U>(p.stage, mask, v, r);  // mask == 0 -> zeros (src/accumulator.cc:426-428)
 #pragma unroll
-    for (int k = 0; k < U; ++k) scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], scale_vec(r[k], s, do_scale));
-  }
-  for (; v0 < p.total_vec; v0 += stride) {
-    uint64_t v[1] = {v0};
-    float4 r[1];
-    reduce_vecs<NR, 1>(p.stage, mask, v, r);
-    scatter_vec(p.dst_tab, s_off, p.ntensors, v0, scale_vec(r[0], s, do_scale));
+      for (int k = 0; k < U; ++k) scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], scale_vec(r[k], s, do_scale));
+    } else {
+      for (uint64_t v0 = base + threadIdx.x; v0 < p.total_vec; v0 += kArThreads) {
+        uint64_t v[1] = {v0};
+        float4 r[1];
+        reduce_vecs<NR, 1>(p.stage, mask, v, r);
+        scatter_vec(p.dst_tab, s_off, p.ntensors, v0, scale_vec(r[0], s, do_scale));
+      }
+    }
   }
   write_result(p, tot);
 }
@@ -423,14 +426,15 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_
   const mb_ar_hdr tot = s_total;
   const bool do_scale = p.scale && tot.num_gradients != 0;
   const float s = reduce_scale(p, tot);
-  const uint64_t stride = (uint64_t)gridDim.x * kArThreads;
-  const uint64_t j0 = (uint64_t)blockIdx.x * kArThreads + threadIdx.x;
+  constexpr int U = Unroll<NR>::value;
+  constexpr uint64_t kChunk = (uint64_t)U * kArThreads;
+  const uint64_t gstride = (uint64_t)gridDim.x * kChunk;
   // phase 1: reduce my slice, write it to my destinations and into every peer's staging (in place: slice `rank` of a
-  // peer's staging is read only by me, and I overwrite an element only after I have loaded it)
+  // peer's staging is read only by me, and I overwrite an element only after I have loaded it).  Chunks are relative
+  // to the slice start so that block b touches the same relative ranges of every slice on every rank.
   {
-    constexpr int U = Unroll<NR>::value;
-    const uint64_t base = (uint64_t)p.rank * p.slice_vec;
-    const uint64_t end = min(p.total_vec, base + p.slice_vec);  // my slice is [base, end)
+    const uint64_t sbase = (uint64_t)p.rank * p.slice_vec;
+    const uint64_t slen = sbase < p.total_vec ? min(p.slice_vec, p.total_vec - sbase) : 0;
     auto emit = [&](uint64_t v, const float4& red) {
       const float4 o = scale_vec(red, s, do_scale);
 #pragma unroll
@@ -438,21 +442,23 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_
         if (q != p.rank) st_f4(p.stage[q] + v * 4, o);
       scatter_vec(p.dst_tab, s_off, p.ntensors, v, o);
     };
-    uint64_t v0 = base + j0;
-    for (; v0 + (uint64_t)(U - 1) * stride < end; v0 += stride * U) {
-      uint64_t v[U];
-      float4 r[U];
+    for (uint64_t cb = (uint64_t)blockIdx.x * kChunk; cb < slen; cb += gstride) {
+      if (cb + kChunk <= slen) {
+        uint64_t v[U];
+        float4 r[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) v[k] = v0 + (uint64_t)k * stride;
-      reduce_vecs<NR, U>(p.stage, mask, v, r);
+        for (int k = 0; k < U; ++k) v[k] = sbase + cb + (uint64_t)k * kArThreads + threadIdx.x;
+        reduce_vecs<NR, U>(p.stage, mask, v, r);
 #pragma unroll
-      for (int k = 0; k < U; ++k) emit(v[k], r[k]);
-    }
-    for (; v0 < end; v0 += stride) {
-      uint64_t v[1] = {v0};
-      float4 r[1];
-      reduce_vecs<NR, 1>(p.stage, mask, v, r);
-      emit(v0, r[0]);
+        for (int k = 0; k < U; ++k) emit(v[k], r[k]);
+      } else {
+        for (uint64_t j = cb + threadIdx.x; j < slen; j += kArThreads) {
+          uint64_t v[1] = {sbase + j};
+          float4 r[1];
+          reduce_vecs<NR, 1>(p.stage, mask, v, r);
+          emit(v[0], r[0]);
+        }
+      }
     }
   }
   if (!block_barrier(p, true)) {
@@ -464,12 +470,14 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_
 #pragma unroll 1
   for (int q = 0; q < NR; ++q) {
     if (q == p.rank) continue;
-    const uint64_t base = (uint64_t)q * p.slice_vec;
-    for (uint64_t j = j0; j < p.slice_vec; j += stride) {
-      const uint64_t v = base + j;
-      if (v >= p.total_vec) break;
-      const float4 r = ld_peer_f4(mine + v * 4);
-      scatter_vec(p.dst_tab, s_off, p.ntensors, v, r);
+    const uint64_t sbase = (uint64_t)q * p.slice_vec;
+    const uint64_t slen = sbase < p.total_vec ? min(p.slice_vec, p.total_vec - sbase) : 0;
+    for (uint64_t cb = (uint64_t)blockIdx.x * kChunk; cb < slen; cb += gstride) {
+      const uint64_t cend = min(cb + kChunk, slen);
+      for (uint64_t j = cb + threadIdx.x; j < cend; j += kArThreads) {
+        const uint64_t v = sbase + j;
+        scatter_vec(p.dst_tab, s_off, p.ntensors, v, ld_peer_f4(mine + v * 4));
+      }
     }
   }
   write_result(p, tot);
@@ -856,7 +864,8 @@ int mb_ar_allreduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* co
   const int sms = sm_count(ctx->device);
   if (sms <= 0) return MB_ECUDA;
   const uint64_t work_vec = twoshot ? p.slice_vec : p.total_vec;
-  uint64_t want = (work_vec + kArThreads - 1) / kArThreads;
+  const uint64_t chunk = (uint64_t)kArThreads * (ctx->world >= 8 ? 1 : ctx->world >= 4 ? 2 : 4);  // Unroll<NR>
+  uint64_t want = (work_vec + chunk - 1) / chunk;
   if (want == 0) want = 1;
   const uint32_t grid = (uint32_t)std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)sms * 2, kArMaxBlocks));
   ArKernel k = kernel_for(ctx->world, twoshot);

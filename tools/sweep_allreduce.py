@@ -68,15 +68,19 @@ def main():
             # (a) whole round = stage kernel + allreduce kernel, (b) allreduce kernel alone.
             def timed(stage):
                 dist.barrier()
-                s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s0.record()
-                for _ in range(args.reps):
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.reps + 1)]
+                evs[0].record()
+                for i in range(args.reps):
                     one_round(stage)
-                e0.record()
-                e0.synchronize()
-                return s0.elapsed_time(e0)
+                    evs[i + 1].record()
+                evs[-1].synchronize()
+                per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.reps))
+                spread[0] = (per[0], per[len(per) // 2], per[-1])
+                return evs[0].elapsed_time(evs[-1])
+            spread = [None]
             t_round = timed(True)
             t_kernel = timed(False)
+            k_spread = spread[0]
             one_round(True)  # leave a valid result behind for the exactness check
             torch.cuda.synchronize()
             ok = bool((dst == world * (world + 1) / 2).all().item())
@@ -91,7 +95,8 @@ def main():
                        "kernel_us": round(t[1].item() * 1e3, 2),
                        "algbw_gbs": round(S / t[1].item() / 1e6, 2), "busbw_gbs": round(S / t[1].item() / 1e6 * bus, 2),
                        "ingress_gbs": round(S * (world - 1) / t[1].item() / 1e6, 2) if name == "oneshot" else None,
-                       "exact": bool(okt.item())}
+                       "exact": bool(okt.item()),
+                       "kernel_us_min_med_max": [round(x * 1e3, 1) for x in k_spread]}
                 results.append(rec)
                 print(json.dumps(rec), flush=True)
         if nccl_group is not None:
