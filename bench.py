@@ -231,16 +231,25 @@ def run_ours(args):
 
     wait_for_full_group()
 
+    def dbg(msg):
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"[rank {rank}] t={time.time() % 1000:.2f} {msg}", file=sys.stderr, flush=True)
+
     for mode in ("value", "e2e"):
         flags.host_obs = mode == "e2e"
         flags.read_metrics = mode == "e2e"
+        dbg(f"{mode}: creating env pool")
         envs = impala.SyntheticEnvPool(flags, device)
+        dbg(f"{mode}: env pool ready")
         state = {"t0": None}
         start_evt, end_evt = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(local) if (rank == 0 and mode == "value") else None
 
         def on_step(res, mode=mode, state=state, start_evt=start_evt, end_evt=end_evt, sampler=sampler):
             n = res.optimizer_steps
+            if os.environ.get("BENCH_DEBUG"):
+                print(f"[rank {rank}] {mode} step {n} t={time.time() % 1000:.2f} actor={res.actor_steps}",
+                      file=sys.stderr, flush=True)
             if n == W:
                 torch.cuda.synchronize()
                 barrier()
@@ -254,7 +263,9 @@ def run_ours(args):
                 return True
             if n == W + K:
                 end_evt.record()
+                dbg(f"{mode}: end recorded, synchronizing")
                 torch.cuda.synchronize()
+                dbg(f"{mode}: synchronized")
                 state["t1"] = time.perf_counter()
                 state["launches"] = _C.kernel_launches() - state["launch0"]
                 state["actor_steps"] = res.actor_steps - state["actor0"]
@@ -265,6 +276,7 @@ def run_ours(args):
 
         res = impala.run_learner(api, flags, acc, model, optimizer, envs, on_step, max_seconds=3600, group=group,
                                  broker=broker, hooks=timer)
+        dbg(f"{mode}: loop finished")
         ms = start_evt.elapsed_time(end_evt)
         wall = (state["t1"] - state["t0"]) * 1e3
         t = torch.tensor([ms, wall], dtype=torch.float64)
@@ -281,7 +293,9 @@ def run_ours(args):
         for _ in range(50):
             pump()
             time.sleep(0.001)
+        dbg(f"{mode}: drained")
         barrier()
+        dbg(f"{mode}: barrier passed")
 
     if rank == 0:
         v, e = results["value"], results["e2e"]
@@ -437,6 +451,9 @@ def run_reference(args):
 
 def main():
     args = parse_args()
+    if os.environ.get("BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BENCH_DEBUG"]), repeat=False, file=sys.stderr)
     if args.impl == "reference":
         run_reference(args)
     else:

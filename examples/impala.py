@@ -11,8 +11,12 @@ ALE environments replaced by a synthetic observation source with the EnvPool res
 atari ResNet: 15 conv + 3 linear layers, 1,094,476 parameters) and the V-trace loss are plain PyTorch: they are the
 workload, not the product.
 """
+import os
+import sys
 import time
 from dataclasses import dataclass
+
+_DEBUG = bool(os.environ.get("BENCH_DEBUG"))
 
 import torch
 import torch.nn as nn
@@ -217,10 +221,16 @@ class LearnerLoop:
         self.res = LearnerResult()
         self.next_env_index = 0
         self.grad_norm_dev = torch.zeros((), device=self.device)
+        self._last_dbg = time.time()
 
     def tick(self):
         """One loop iteration.  Returns True when it performed an optimizer step."""
         flags, acc, model = self.flags, self.acc, self.model
+        if _DEBUG and time.time() - self._last_dbg > 5 and hasattr(acc, "debug_state"):
+            self._last_dbg = time.time()
+            print(f"[dbg pid {os.getpid()}] steps={self.res.optimizer_steps} actor={self.res.actor_steps} "
+                  f"queued={self.learn_batcher.size()} connected={acc.connected()} wants={acc.wants_gradients()} "
+                  f"{acc.debug_state()}", file=sys.stderr, flush=True)
         if self.broker is not None:
             self.broker.update()
         if self.group is not None:

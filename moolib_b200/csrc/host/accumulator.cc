@@ -242,7 +242,9 @@ class Accumulator {
 
   // reference: reduceImpl, src/accumulator.cc:880-1003
   void reduceImpl(int batchSize) {
+    MBH_PHASE("reduceImpl:enter");
     std::lock_guard<std::mutex> l(mu_);
+    MBH_PHASE("reduceImpl:locked");
     if (!wantsGradientsLocked())
       throw std::runtime_error("reduceGradients/skipGradients called while wantsGradients() is false");
     size_t index = nextIndex_;
@@ -290,12 +292,14 @@ class Accumulator {
       if (target->isCounting) target->wantsMoreCounting = true;
       else startCount(target);
     }
+    MBH_PHASE("idle");
   }
   void reduceGradients(int batchSize) { reduceImpl(batchSize); }
   void skipGradients() { reduceImpl(0); }
 
   // reference: startCount, src/accumulator.cc:1035-1078
   void startCount(const std::shared_ptr<ReduceSlot>& target) {
+    MBH_PHASE("startCount");
     if (target->syncId != hSyncId_ || target->syncId != parts_.info->syncId.load()) return;
     target->isCounting = true;
     try {
@@ -313,6 +317,7 @@ class Accumulator {
 
   // reference: startReduce, src/accumulator.cc:1005-1033
   void startReduce(const std::shared_ptr<ReduceSlot>& target) {
+    MBH_PHASE("startReduce");
     if (target->syncId != hSyncId_ || target->syncId != parts_.info->syncId.load()) return;
     target->reduceStarted = true;
     target->reduceStart = Clock::now();
@@ -365,9 +370,10 @@ class Accumulator {
       auto op = std::move(v->countOp);
       v->countOp.reset();
       ran = true;
-      std::lock_guard<std::mutex> fl(op->future->mu);
-      if (op->future->flags & 1) {
-        Reader r(op->future->value);
+      Bytes value;
+      const int flags = op->future->snapshot(&value, nullptr);  // no lock held while we start the next operation
+      if (flags & 1) {
+        Reader r(value);
         uint64_t size = r.u64();
         if (size >= virtualBatchSize_) {
           if (v->syncId == hSyncId_ && v->syncId == parts_.info->syncId.load()) {
@@ -402,10 +408,11 @@ class Accumulator {
       auto op = std::move(v->reduceOp);
       v->reduceOp.reset();
       ran = true;
-      std::lock_guard<std::mutex> fl(op->future->mu);
-      if (op->future->flags & 1) {
+      Bytes value;
+      const int flags = op->future->snapshot(&value, nullptr);
+      if (flags & 1) {
         torch::NoGradGuard ng;
-        Reduction red = unpackReduction(op->future->value);
+        Reduction red = unpackReduction(value);
         if (red.grads.empty()) {
           actuallyZeroGradients();
         } else if (red.h.num_gradients) {
@@ -504,6 +511,7 @@ class Accumulator {
   }
 
   void setState(py::object userState) {
+    MBH_PHASE("setState");
     userState = deepCopyToCpu(userState);
     Bytes pickled = pickleDumps(userState);
     std::lock_guard<std::mutex> l(mu_);
@@ -563,6 +571,7 @@ class Accumulator {
   }
 
   void commitModelUpdate() {
+    MBH_PHASE("commitModelUpdate");
     torch::NoGradGuard ng;
     std::vector<Bytes> ps, bs;
     Bytes state;
@@ -600,6 +609,7 @@ class Accumulator {
   // ---- update (src/accumulator.cc:519-665) -------------------------------------------------------------------------
   void update() {
     torch::NoGradGuard ng;
+    MBH_PHASE("update:enter");
     if (shouldUpdateGroup_) {
       py::gil_scoped_release nogil;
       parts_.service->update(*parts_.info, 0, 10 * 1000);
@@ -607,13 +617,15 @@ class Accumulator {
     std::lock_guard<std::mutex> l(mu_);
     auto now = Clock::now();
 
+    MBH_PHASE("update:locked");
     // leader election result
     if (findLeaderOp_ && findLeaderOp_->future->done()) {
       auto op = std::move(findLeaderOp_);
       findLeaderOp_.reset();
-      std::lock_guard<std::mutex> fl(op->future->mu);
-      if (op->future->flags & 1) {
-        Reader r(op->future->value);
+      Bytes value;
+      const int flags = op->future->snapshot(&value, nullptr);
+      if (flags & 1) {
+        Reader r(value);
         int64_t version = r.i64();
         std::string leader = r.str();
         isFindingLeader_ = false;
@@ -628,12 +640,15 @@ class Accumulator {
         resync();
       }
     }
+    MBH_PHASE("update:reducer-poll");
     if (gradsOnCuda_ && hSyncId_ != 0 && !reducerReady_) {
       auto r = reducer();
       if (r->failed()) throw std::runtime_error(r->error());
       reducerReady_ = r->poll() && r->syncId() == hSyncId_;
     }
+    MBH_PHASE("update:checkGradientResult");
     checkGradientResult();
+    MBH_PHASE("update:after-check");
 
     uint32_t groupSync = parts_.info->syncId.load();
     if (hSyncId_ != groupSync) {
@@ -684,6 +699,7 @@ class Accumulator {
       netModelVersion_ = modelVersion_;
       netWaitingForModel_ = isWaitingForModel_;
     }
+    MBH_PHASE("update:model-sync");
     if (haveParams) {
       bool ignore;
       {
@@ -703,10 +719,42 @@ class Accumulator {
       resync();
     }
     if (haveBuffers && !haveParams) commitBuffersUpdate();
+    MBH_PHASE("update:sendModelUpdates");
     if (!members_.empty()) sendModelUpdates();
+    MBH_PHASE("idle");
   }
 
   // ---- misc API --------------------------------------------------------------------------------------------------
+  py::dict debugState() {
+    std::lock_guard<std::mutex> l(mu_);
+    py::dict d;
+    d["sync_id"] = hSyncId_;
+    d["group_sync_id"] = parts_.info->syncId.load();
+    d["leader"] = syncLeader_;
+    d["members"] = members_.size();
+    d["finding_leader"] = isFindingLeader_;
+    d["waiting_for_model"] = isWaitingForModel_;
+    d["has_received_model"] = hasReceivedModel_;
+    d["has_gradients"] = hasGradients_;
+    d["reducer_ready"] = reducerReady_;
+    d["reducer_failed"] = reducer_ ? reducer_->failed() : false;
+    d["reducer_sync"] = reducer_ ? reducer_->syncId() : 0u;
+    d["model_version"] = modelVersion_;
+    d["last_error"] = lastError_;
+    d["next_index"] = nextIndex_;
+    auto& v = slots_[nextResultIndex_];
+    if (v) {
+      d["slot_counting"] = v->isCounting;
+      d["slot_count_op"] = (bool)v->countOp;
+      d["slot_reduce_started"] = v->reduceStarted;
+      d["slot_reduce_done"] = v->reduceDone;
+      d["slot_kernel_in_flight"] = v->kernelInFlight;
+      d["slot_num_gradients"] = v->data.num_gradients;
+      d["slot_num_skipped"] = v->data.num_skipped;
+      d["slot_batch"] = v->data.batch_size;
+    }
+    return d;
+  }
   py::dict getGradientStats() {
     py::dict r;
     r["num_gradients"] = stats_.num_gradients;
@@ -802,7 +850,8 @@ void bind_accumulator(py::module_& m) {
       .def("set_parallel_gradients", &Accumulator::setParallelGradients)
       .def("get_leader", &Accumulator::getLeader)
       .def("is_leader", &Accumulator::isLeader)
-      .def("get_gradient_stats", &Accumulator::getGradientStats);
+      .def("get_gradient_stats", &Accumulator::getGradientStats)
+      .def("debug_state", &Accumulator::debugState);
 }
 
 }  // namespace mbh

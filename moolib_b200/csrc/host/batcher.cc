@@ -7,7 +7,13 @@
 // stream.  CPU batchers (device="cpu") keep using at::copy_: they are API parity, not the hot path.
 #include "common.h"
 
+#include <unistd.h>
+
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <cstdlib>
+#include <thread>
 #include <deque>
 #include <mutex>
 #include <optional>
@@ -17,6 +23,37 @@ namespace mbh {
 uint64_t& launch_counter() {
   static uint64_t n = 0;
   return n;
+}
+
+namespace {
+std::atomic<const char*> g_phase{"idle"};
+std::atomic<int64_t> g_phase_ns{0};
+}  // namespace
+
+void trace_phase(const char* phase) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("MOOLIB_B200_TRACE");
+    if (!e || !*e || *e == '0') return false;
+    std::thread([] {
+      const char* last = nullptr;
+      while (true) {
+        std::this_thread::sleep_for(std::chrono::seconds(1));
+        const char* ph = g_phase.load();
+        int64_t age = std::chrono::steady_clock::now().time_since_epoch().count() - g_phase_ns.load();
+        if (age > 3000000000ll && ph != last) {
+          fprintf(stderr, "[moolib_b200 trace pid %d] stuck %.1f s in phase '%s'\n", (int)getpid(), age / 1e9, ph);
+          fflush(stderr);
+          last = ph;
+        } else if (age <= 3000000000ll) {
+          last = nullptr;
+        }
+      }
+    }).detach();
+    return true;
+  }();
+  if (!enabled) return;
+  g_phase.store(phase);
+  g_phase_ns.store(std::chrono::steady_clock::now().time_since_epoch().count());
 }
 
 namespace {

@@ -37,6 +37,11 @@ inline bool is_tensor(const py::handle& h) { return THPVariable_Check(h.ptr()); 
 inline torch::Tensor to_tensor(const py::handle& h) { return THPVariable_Unpack(h.ptr()); }
 inline py::object to_python(const torch::Tensor& t) { return py::reinterpret_steal<py::object>(THPVariable_Wrap(t)); }
 
+// Debug aid (MOOLIB_B200_TRACE=1): the host layer records the phase it is in; a watchdog thread prints it whenever it
+// has not changed for 3 s.  Costs one relaxed store per phase when disabled.
+void trace_phase(const char* phase);
+#define MBH_PHASE(name) ::mbh::trace_phase(name)
+
 // Number of kernels this process launched through the host layer (bench.py's gpu_launches claim).
 uint64_t& launch_counter();
 

@@ -153,6 +153,14 @@ struct FutureState {
   void cancel();
   bool done();
   bool wait(double seconds);  // < 0: forever
+  // Snapshot (flags, value, error) without keeping the lock: callers must not hold `mu` while they start new operations
+  // (GroupService::allReduce inspects the previous op of the same name, i.e. possibly this very future).
+  int snapshot(Bytes* v, std::string* e) {
+    std::lock_guard<std::mutex> l(mu);
+    if (v && (flags & 1)) *v = value;
+    if (e) *e = error;
+    return flags;
+  }
 };
 
 // ---- group membership -------------------------------------------------------------------------------------------

@@ -113,14 +113,14 @@ bool DeviceReducer::poll() {
   if (failed_ || !exchange_) return false;
   auto& st = *exchange_->future;
   if (!st.done()) return false;
-  std::lock_guard<std::mutex> l(st.mu);
-  if (!(st.flags & 1)) {
+  Bytes gathered;
+  if (!(st.snapshot(&gathered, nullptr) & 1)) {
     // cancelled by a group change or timed out: a new epoch will follow
     exchange_.reset();
     syncId_ = 0;
     return false;
   }
-  Reader r(st.value);
+  Reader r(gathered);
   int imported = 0;
   while (!r.done()) {
     int peer = (int)r.u64();
@@ -216,8 +216,8 @@ struct TensorReduceOp {
         auto& g = *gate->future;
         if (!g.done()) return;
         {
-          std::lock_guard<std::mutex> l(g.mu);
-          if (!(g.flags & 1)) return fail(g.error.empty() ? "AllReduce operation cancelled" : g.error);
+          std::string err;
+          if (!(g.snapshot(nullptr, &err) & 1)) return fail(err.empty() ? "AllReduce operation cancelled" : err);
         }
         // everyone is here: one stage launch + one allreduce launch on the caller's stream
         c10::cuda::CUDAGuard dg(reducer->device());

@@ -112,6 +112,7 @@ void GroupService::resync(GroupInfo& g) {
 // Mirrors GroupService::update (src/group.h:393-490): ping cadence, broker-silence detection, adoption of a pushed
 // member list, cancellation / timeout of in-flight allreduces.
 bool GroupService::update(GroupInfo& g, int32_t sortOrder, uint32_t timeoutMs) {
+  MBH_PHASE("GroupService::update");
   auto now = Clock::now();
   std::vector<std::shared_ptr<SmallReduce>> cancelled, timedOut;
   bool updated;
@@ -186,6 +187,7 @@ bool GroupService::update(GroupInfo& g, int32_t sortOrder, uint32_t timeoutMs) {
   }
   for (auto& h : cancelled) h->future->setError("AllReduce operation cancelled due to a group change");
   for (auto& h : timedOut) h->future->setError("AllReduce operation timed out");
+  MBH_PHASE("idle");
   return updated;
 }
 
@@ -193,6 +195,7 @@ bool GroupService::update(GroupInfo& g, int32_t sortOrder, uint32_t timeoutMs) {
 
 std::shared_ptr<SmallReduce> GroupService::allReduce(std::shared_ptr<GroupInfo> g, const std::string& name, Bytes value,
                                                      std::function<Bytes(const Bytes&, const Bytes&)> op) {
+  MBH_PHASE("GroupService::allReduce");
   auto r = std::make_shared<SmallReduce>();
   r->future = std::make_shared<FutureState>();
   r->op = std::move(op);
@@ -376,6 +379,7 @@ BrokerService::~BrokerService() {
 }
 
 void BrokerService::update() {
+  MBH_PHASE("BrokerService::update");
   auto now = Clock::now();
   struct Push {
     std::string peer, service;

@@ -18,6 +18,9 @@
 
 namespace mbh {
 
+void trace_phase(const char* phase);
+static void mbh_trace_phase_hook(const char* p) { trace_phase(p); }
+
 namespace {
 constexpr uint32_t kHello = 1, kRoute = 2;
 constexpr size_t kMaxFrame = 1u << 30;
@@ -214,6 +217,7 @@ void RpcCore::unhandle(const std::string& service) {
 
 bool RpcCore::writeFrame(Conn& c, const Bytes& body) {
   std::lock_guard<std::mutex> l(c.wmu);
+  if (std::this_thread::get_id() != thread_.get_id()) mbh_trace_phase_hook("RpcCore::writeFrame(caller thread)");
   if (c.dead) return false;
   uint32_t len = (uint32_t)body.size();
   iovec iov[2] = {{&len, 4}, {const_cast<char*>(body.data()), body.size()}};

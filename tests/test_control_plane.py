@@ -261,3 +261,32 @@ def test_reduce_without_wants_gradients_is_an_error():
     assert not a.wants_gradients()
     with pytest.raises(RuntimeError, match="called while wantsGradients\\(\\) is false"):
         a.reduce_gradients(1)
+
+
+@pytest.mark.timeout(120)
+def test_recount_after_failed_count_does_not_deadlock():
+    """A peer that contributes again while a count is in flight sets wantsMoreCounting; when that count comes back
+    below the virtual batch size the next count is started from inside the result handling (src/accumulator.cc:
+    1066-1071).  Regression test: this used to self-deadlock on the finished op's future mutex."""
+    c = Cluster(2, group="recount")
+    c.form()
+    models, accs = _make_accumulators(c, 2, 50)
+    for a in accs:
+        a.set_virtual_batch_size(50)
+    rounds = 0
+    t0 = time.time()
+    while rounds < 3:
+        for i, (m, a) in enumerate(zip(models, accs)):
+            # several contributions per pump: the 2nd..4th arrive while the first count is still in flight
+            for _ in range(4):
+                if a.wants_gradients():
+                    m.weight.grad = torch.ones_like(m.weight)
+                    m.bias.grad = torch.ones_like(m.bias)
+                    a.reduce_gradients(5)
+        c.pump(accs)
+        for m, a in zip(models, accs):
+            if a.has_gradients():
+                assert (m.weight.grad == 1).all()
+                a.zero_gradients()
+                rounds += 1
+        assert time.time() - t0 < 90
