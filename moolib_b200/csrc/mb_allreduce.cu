@@ -123,7 +123,7 @@ struct ArParams {
   int32_t rank;
   int32_t world;
   int32_t scale;
-  int32_t pad_;
+  int32_t force_u1;  // tuning aid: disable the U-way unrolled path
   HostResult* result;
   const uint32_t* abort_flag;
   uint64_t timeout_ns;
@@ -367,7 +367,7 @@ __device__ __forceinline__ void write_result(const ArParams& p, const mb_ar_hdr&
 // ---- K-A2 one-shot ----------------------------------------------------------------------------------------------
 
 template <int NR>
-__global__ void __launch_bounds__(kArThreads, 2) ar_oneshot_kernel(const __grid_constant__ ArParams p) {
+__global__ void __launch_bounds__(kArThreads, 1) ar_oneshot_kernel(const __grid_constant__ ArParams p) {
   __shared__ uint32_t s_off[kArMaxTensors];
   __shared__ mb_ar_hdr s_total;
   __shared__ uint32_t s_mask;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_oneshot_kernel(const __grid_
   constexpr int U = Unroll<NR>::value;
   constexpr uint64_t kChunk = (uint64_t)U * kArThreads;
   for (uint64_t base = (uint64_t)blockIdx.x * kChunk; base < p.total_vec; base += (uint64_t)gridDim.x * kChunk) {
-    if (base + kChunk <= p.total_vec) {
+    if (base + kChunk <= p.total_vec && !p.force_u1) {
       uint64_t v[U];
       float4 r[U];
 #pragma unroll
@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_oneshot_kernel(const __grid_
 #pragma unroll
       for (int k = 0; k < U; ++k) scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], scale_vec(r[k], s, do_scale));
     } else {
-      for (uint64_t v0 = base + threadIdx.x; v0 < p.total_vec; v0 += kArThreads) {
+      const uint64_t cend = min(base + kChunk, p.total_vec);
+      for (uint64_t v0 = base + threadIdx.x; v0 < cend; v0 += kArThreads) {
         uint64_t v[1] = {v0};
         float4 r[1];
         reduce_vecs<NR, 1>(p.stage, mask, v, r);
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_oneshot_kernel(const __grid_
 // ---- K-A2 two-shot ----------------------------------------------------------------------------------------------
 
 template <int NR>
-__global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_constant__ ArParams p) {
+__global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_constant__ ArParams p) {
   __shared__ uint32_t s_off[kArMaxTensors];
   __shared__ mb_ar_hdr s_total;
   __shared__ uint32_t s_mask;
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_
       scatter_vec(p.dst_tab, s_off, p.ntensors, v, o);
     };
     for (uint64_t cb = (uint64_t)blockIdx.x * kChunk; cb < slen; cb += gstride) {
-      if (cb + kChunk <= slen) {
+      if (cb + kChunk <= slen && !p.force_u1) {
         uint64_t v[U];
         float4 r[U];
 #pragma unroll
@@ -452,7 +453,8 @@ __global__ void __launch_bounds__(kArThreads, 2) ar_twoshot_kernel(const __grid_
 #pragma unroll
         for (int k = 0; k < U; ++k) emit(v[k], r[k]);
       } else {
-        for (uint64_t j = cb + threadIdx.x; j < slen; j += kArThreads) {
+        const uint64_t cend = min(cb + kChunk, slen);
+        for (uint64_t j = cb + threadIdx.x; j < cend; j += kArThreads) {
           uint64_t v[1] = {sbase + j};
           float4 r[1];
           reduce_vecs<NR, 1>(p.stage, mask, v, r);
@@ -867,7 +869,12 @@ int mb_ar_allreduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* co
   const uint64_t chunk = (uint64_t)kArThreads * (ctx->world >= 8 ? 1 : ctx->world >= 4 ? 2 : 4);  // Unroll<NR>
   uint64_t want = (work_vec + chunk - 1) / chunk;
   if (want == 0) want = 1;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)sms * 2, kArMaxBlocks));
+  // One CTA per SM: with two, the per-block barrier pairs (block b <-> block b on every peer) run in two waves that start
+  // at different times on different GPUs; measured on 2 B200: 8-64 MB rounds became bimodal (43 us vs 370 us).
+  static const uint64_t blocks_per_sm = env_u64("MB_AR_BLOCKS_PER_SM", 1);
+  static const uint64_t force_u1 = env_u64("MB_AR_FORCE_U1", 0);
+  p.force_u1 = (int32_t)force_u1;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, kArMaxBlocks));
   ArKernel k = kernel_for(ctx->world, twoshot);
   k<<<grid, kArThreads, 0, stream>>>(p);
   MB_CUDA(cudaGetLastError());
