@@ -8,7 +8,5 @@ PYBIND11_MODULE(_C, m) {
   mbh::bind_batcher(m);
   mbh::bind_rpc(m);
   mbh::bind_accumulator(m);
-#ifdef MBH_WITH_ENVPOOL
   mbh::bind_envpool(m);
-#endif
 }

@@ -255,11 +255,31 @@ def make_accumulator():
         print("  ", r)
 
 
+def make_envpool():
+    """Reference EnvPool (forked workers + POSIX shm) stepping tests/envs_for_tests.FrameEnv with seeded actions."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from envs_for_tests import FrameEnv
+    bs, steps = 6, 24
+    envs = moolib.EnvPool(FrameEnv, num_processes=3, batch_size=bs, num_batches=2)
+    rng = np.random.Generator(np.random.PCG64(77))
+    out = {"bs": np.array(bs), "steps": np.array(steps)}
+    for t in range(steps):
+        action = torch.from_numpy(rng.integers(0, 18, size=bs, dtype=np.int64))
+        obs = envs.step(t % 2, action).result()
+        out[f"state{t}"] = obs["state"].numpy().copy()
+        out[f"reward{t}"] = obs["reward"].numpy().copy()
+        out[f"done{t}"] = obs["done"].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "envpool_golden.npz"), **out)
+    print("envpool:", steps, "steps of", bs, "envs")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["batcher", "allreduce", "accumulator"]
+    which = sys.argv[1:] or ["batcher", "allreduce", "accumulator", "envpool"]
     if "batcher" in which:
         make_batcher()
     if "allreduce" in which:
         make_allreduce()
     if "accumulator" in which:
         make_accumulator()
+    if "envpool" in which:
+        make_envpool()
