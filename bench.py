@@ -257,6 +257,8 @@ def run_ours(args):
                     sampler.start()
                 state["launch0"] = _C.kernel_launches()
                 state["actor0"] = res.actor_steps
+                state["frames0"] = res.env_train_steps
+                state["stats0"] = (res.t_learn, res.t_act, res.t_opt, res.t_idle, res.n_learn, res.n_skip, res.n_idle)
                 timer.enabled = mode == "value"
                 state["t0"] = time.perf_counter()
                 start_evt.record()
@@ -269,6 +271,11 @@ def run_ours(args):
                 state["t1"] = time.perf_counter()
                 state["launches"] = _C.kernel_launches() - state["launch0"]
                 state["actor_steps"] = res.actor_steps - state["actor0"]
+                state["frames"] = res.env_train_steps - state["frames0"]
+                s0 = state["stats0"]
+                s1 = (res.t_learn, res.t_act, res.t_opt, res.t_idle, res.n_learn, res.n_skip, res.n_idle)
+                state["loop"] = {k: round(b - a, 4) for k, a, b in zip(
+                    ("t_learn_s", "t_act_s", "t_opt_s", "t_idle_s", "n_learn", "n_skip", "n_idle"), s0, s1)}
                 timer.enabled = False
                 barrier()
                 return False
@@ -280,10 +287,16 @@ def run_ours(args):
         ms = start_evt.elapsed_time(end_evt)
         wall = (state["t1"] - state["t0"]) * 1e3
         t = torch.tensor([ms, wall], dtype=torch.float64)
+        fr = torch.tensor([float(state["frames"])], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        frames = flags.unroll_length * flags.batch_size * K * world
+            dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+        # frames = the reference's env_train_steps (examples/vtrace/experiment.py:155): unroll_length * batch_size per
+        # gradient batch computed, summed over all learners.  With virtual_batch_size == batch_size * N it equals
+        # unroll_length * batch_size * N * optimizer_steps whenever every learner contributes exactly once per round.
+        frames = fr[0].item()
         results[mode] = {"ms": t[0].item(), "wall_ms": t[1].item(), "frames": frames,
+                         "frames_per_opt_step": frames / max(K, 1), "loop": state["loop"],
                          "value": frames / (t[0].item() / 1e3), "launches": state["launches"],
                          "actor_steps": state["actor_steps"], "loss": float(res.last_loss),
                          "h2d": envs.h2d_bytes, "d2h": envs.d2h_bytes}
@@ -321,6 +334,9 @@ def run_ours(args):
                          "traffic": None, "peak_kind": peak_kind, "per_op": ops},
             "clocks": results.get("clocks"),
             "wall_ms_per_step": round(v["wall_ms"] / K, 4),
+            "frames_per_opt_step": {"value": v["frames_per_opt_step"], "e2e": e["frames_per_opt_step"],
+                                    "nominal": 640 * world},
+            "loop_stats_rank0": {"value": v["loop"], "e2e": e["loop"]},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
@@ -387,7 +403,10 @@ def run_reference(args):
     n_peers = max(world, args.gpus) if not use_cuda else 1
     device = "cuda:0" if use_cuda else "cpu"
     cores = os.cpu_count()
-    torch.set_num_threads(max(1, cores // n_peers))
+    # ATen's CPU kernels stop scaling (and start thrashing) far below the core count of a 128-core host for these
+    # small convolutions; the reference's own scheduler also takes min(cores-1, 64) threads (src/async.cc:67-83)
+    threads = max(1, min(cores, 32) // n_peers)
+    torch.set_num_threads(threads)
     K, W = args.steps, args.warmup
     port = 29400 + 57 + (os.getpid() % 500)
     addr = f"127.0.0.1:{port}"
@@ -420,6 +439,7 @@ def run_reference(args):
             sync()
             t0 = time.perf_counter()
             base = [lp.res.optimizer_steps for lp in loops]
+            base_frames = [lp.res.env_train_steps for lp in loops]
         if t0 is not None:
             done_steps = min(lp.res.optimizer_steps - b for lp, b in zip(loops, base))
             if done_steps >= K or time.time() - t_begin > args.max_seconds:
@@ -432,7 +452,7 @@ def run_reference(args):
         return
     dt = time.perf_counter() - t0
     total_steps = sum(lp.res.optimizer_steps - b for lp, b in zip(loops, base))
-    frames = 20 * 32 * total_steps
+    frames = sum(lp.res.env_train_steps - b for lp, b in zip(loops, base_frames))  # experiment.py:155
     value = frames / dt
     sample = (f"{done_steps} of {K} optimizer steps per peer x {n_peers} peer(s) in one process, device={device}, "
               f"full config (256 envs, T=21, batch 32), {dt:.1f} s")
@@ -443,7 +463,7 @@ def run_reference(args):
                                    f"reference moolib ({'oracle/_ref_cuda, model on cuda:0' if use_cuda else 'oracle/_ref, host cores'})",
                        "global_batch": 32 * n_peers, "parallelism": f"dp{n_peers}"},
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
-                             "sample": sample},
+                             "sample": sample, "aten_threads_per_peer": threads},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     os._exit(0)  # the reference's RPC threads do not always join cleanly at interpreter exit

@@ -193,6 +193,9 @@ class LearnerResult:
         self.actor_steps = 0
         self.last_loss = None
         self.grad_norm_sum = 0.0
+        # where the host thread spends its ticks (wall seconds, counts)
+        self.t_learn = self.t_act = self.t_opt = self.t_idle = 0.0
+        self.n_learn = self.n_skip = self.n_idle = 0
 
 
 class LearnerLoop:
@@ -247,6 +250,7 @@ class LearnerLoop:
         if not acc.connected():
             time.sleep(0.0005)
             return False
+        t_tick = time.perf_counter()
         if acc.has_gradients():
             norm = nn.utils.clip_grad_norm_(model.parameters(), flags.grad_norm_clipping)
             self.opt.step()
@@ -256,18 +260,24 @@ class LearnerLoop:
                 self.grad_norm_dev += norm
             acc.zero_gradients()
             self.res.optimizer_steps += 1
+            self.res.t_opt += time.perf_counter() - t_tick
             return True
         if not self.learn_batcher.empty() and acc.wants_gradients():
             self.res.last_loss = compute_gradients(model, self.learn_batcher.get(), flags)
             self.res.env_train_steps += flags.unroll_length * flags.batch_size
             acc.reduce_gradients(flags.batch_size)
+            self.res.n_learn += 1
+            self.res.t_learn += time.perf_counter() - t_tick
             return False
         if acc.wants_gradients():
             acc.skip_gradients()
+            self.res.n_skip += 1
         if self.learn_batcher.size() >= self.flags.max_queued_batches:
             # (not in the reference loop) never let unconsumed learner batches pile up in device memory while the
             # accumulator is not asking for gradients
             time.sleep(0.0002)
+            self.res.n_idle += 1
+            self.res.t_idle += time.perf_counter() - t_tick
             return False
         cur = self.next_env_index
         self.next_env_index = (self.next_env_index + 1) % flags.num_actor_batches
@@ -295,6 +305,7 @@ class LearnerLoop:
             self._cat(self.learn_batcher, data)
             es.initial_core_state = prev_core_state
             self._stack(es.time_batcher, last_data)
+        self.res.t_act += time.perf_counter() - t_tick
         return False
 
     def _stack(self, batcher, item):

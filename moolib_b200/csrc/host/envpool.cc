@@ -358,6 +358,14 @@ class EnvStepper : public std::enable_shared_from_this<EnvStepper> {
                                 "EnvPool.step");
       keepAction_[bufferIndex] = a;  // alive until the kernel has run
     } else {
+      // Host-written mailboxes release the workers immediately.  If the slabs are pinned/mapped, device reads of the
+      // previous result (async H2D copies, Batcher kernels) may still be queued: wait for them before the workers may
+      // overwrite the slab.  (With CUDA actions this ordering is free: the scatter kernel above is enqueued behind
+      // those reads on the same stream.)
+      if (!registered_.empty()) {
+        py::gil_scoped_release nogil;
+        cudaStreamSynchronize(c10::cuda::getCurrentCUDAStream().stream());
+      }
       torch::Tensor a = action.contiguous();
       const int64_t* acc = a.data_ptr<int64_t>();
       for (size_t i = 0; i < size; ++i) {
