@@ -338,6 +338,8 @@ def run_learner(api, flags, accumulator, model, optimizer, envs, on_optimizer_st
 
 
 def make_learner(flags):
+    # algorithm selection only (no precision change): let cuDNN pick its fastest kernels for the fixed conv shapes
+    torch.backends.cudnn.benchmark = True
     torch.manual_seed(flags.seed)
     device = torch.device(flags.device)
     model = ImpalaNet(flags.num_actions).to(device)
