@@ -413,8 +413,11 @@ def run_reference(args):
     broker = ref.Broker()
     broker.listen(addr)
     loops = []
+    # N reference peers share ONE host process here (rank 0 only runs this arm): bound the sample by shrinking the actor
+    # pool per peer -- the learner batch (T=21 x 32) and the reduction (N peers, 4.38 MB) are the full-size ones.
+    envs_per_peer = args.envs if n_peers == 1 else max(32, args.envs // n_peers)
     for i in range(n_peers):
-        flags = impala.Flags(actor_batch_size=args.envs, virtual_batch_size=32 * n_peers, device=device,
+        flags = impala.Flags(actor_batch_size=envs_per_peer, virtual_batch_size=32 * n_peers, device=device,
                              host_obs=True, read_metrics=True)
         flags.seed += i
         model, opt = impala.make_learner(flags)
@@ -447,15 +450,15 @@ def run_reference(args):
         elif time.time() - t_begin > args.max_seconds:
             break
     sync()
-    if t0 is None or done_steps == 0:
-        print(json.dumps({"impl": "reference", "unavailable": "no timed step completed within --max-seconds"}))
+    if t0 is None or sum(lp.res.env_train_steps - b for lp, b in zip(loops, base_frames)) == 0:
+        print(json.dumps({"impl": "reference", "unavailable": "no gradient batch completed within --max-seconds"}))
         return
     dt = time.perf_counter() - t0
     total_steps = sum(lp.res.optimizer_steps - b for lp, b in zip(loops, base))
     frames = sum(lp.res.env_train_steps - b for lp, b in zip(loops, base_frames))  # experiment.py:155
     value = frames / dt
     sample = (f"{done_steps} of {K} optimizer steps per peer x {n_peers} peer(s) in one process, device={device}, "
-              f"full config (256 envs, T=21, batch 32), {dt:.1f} s")
+              f"{envs_per_peer} envs per peer, T=21, batch 32 per peer, {dt:.1f} s")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
             "steps": done_steps, "warmup": W, "ms_per_step": round(dt * 1e3 / max(done_steps, 1), 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
