@@ -27,4 +27,47 @@ for _name in ("Accumulator", "Group", "Rpc", "Broker", "EnvPool", "EnvStepper", 
     if hasattr(_C, _name):
         globals()[_name] = getattr(_C, _name)
 
+
+
+# asyncio support (reference: FutureWrapper.__await__ / BatcherWrapper.__await__ / QueueWrapper.__await__,
+# src/moolib.cc:316-393, 1440-1455, 553-576): the native objects are polled from the running event loop.
+def _await_polling(ready, take):
+    import asyncio
+
+    async def _wait():
+        delay = 0.0
+        while not ready():
+            await asyncio.sleep(delay)
+            delay = min(0.002, delay + 0.0002)
+        return take()
+
+    return _wait().__await__()
+
+
+def _future_await(self):
+    return _await_polling(self.done, self.result)
+
+
+def _batcher_await(self):
+    return _await_polling(lambda: not self.empty(), self.get)
+
+
+def _queue_await(self):
+    box = []
+
+    def ready():
+        r = self.try_get()
+        if r is not None:
+            box.append(r)
+        return bool(box)
+
+    return _await_polling(ready, lambda: box.pop())
+
+
+_C.Future.__await__ = _future_await
+_C.Batcher.__await__ = _batcher_await
+if hasattr(_C, "Queue"):
+    _C.Queue.__await__ = _queue_await
+    Queue = _C.Queue
+
 __version__ = "0.1.0"

@@ -504,6 +504,8 @@ std::pair<py::object, bool> squeezeFieldsImpl(const py::handle& input, int64_t d
   return {py::reinterpret_borrow<py::object>(input), false};
 }
 
+}  // namespace
+
 // reference: src/batch_utils.cc:259-315
 py::object stackFields(const py::tuple& input, int64_t dim) {
   if (input.size() == 0) throw std::runtime_error("stack_fields: empty input");
@@ -541,6 +543,8 @@ py::object stackFields(const py::tuple& input, int64_t dim) {
       },
       input[0]);
 }
+
+namespace {
 
 bool prepareForUnstack(const py::handle& input, std::vector<bool>& batchTuple) {
   if (py::isinstance<py::tuple>(input)) {
@@ -607,6 +611,8 @@ py::tuple unstackFieldsImpl(const py::handle& input, int64_t batchSize, int64_t 
   return py::tuple();
 }
 
+}  // namespace
+
 // reference: src/batch_utils.cc:317-325
 py::tuple unstackFields(const py::handle& input, int64_t batchSize, int64_t dim) {
   if (batchSize == 1) return py::make_tuple(squeezeFieldsImpl(input, dim).first);
@@ -615,8 +621,6 @@ py::tuple unstackFields(const py::handle& input, int64_t batchSize, int64_t dim)
   size_t tupleIndex = 0;
   return unstackFieldsImpl(input, batchSize, dim, batchTuple, tupleIndex);
 }
-
-}  // namespace
 
 void bind_batcher(py::module_& m) {
   py::class_<BatcherWrapper>(m, "Batcher",

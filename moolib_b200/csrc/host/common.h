@@ -51,6 +51,10 @@ torch::Tensor unpackTensor(const std::string& b);
 std::string pickleDumps(const py::handle& o);
 py::object pickleLoads(const std::string& b);
 
+// utils::stackFields / unstackFields (reference: src/batch_utils.cc:259-325), implemented in batcher.cc
+py::object stackFields(const py::tuple& input, int64_t dim);
+py::tuple unstackFields(const py::handle& input, int64_t batchSize, int64_t dim);
+
 void bind_batcher(py::module_& m);
 void bind_accumulator(py::module_& m);
 void bind_envpool(py::module_& m);

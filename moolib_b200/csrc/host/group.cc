@@ -498,8 +498,115 @@ torch::Tensor unpackTensor(const Bytes& b) {
   return t;
 }
 
+// reference: QueueWrapper (src/moolib.cc:433-576) -- calls to a function defined with define_queue() are parked here and
+// handed to the user as (return_callback, args, kwargs); with dynamic batching up to batch_size parked calls are merged
+// with utils::stackFields (src/moolib.cc:492) and the single result is split again with unstackFields (:499).
+struct PyQueue {
+  struct Entry {
+    std::string src;
+    uint64_t id;
+    py::object args, kwargs;
+    Clock::time_point t;
+  };
+  std::weak_ptr<RpcCore> core;
+  int64_t batchSize = 0;
+  bool dynamicBatching = false;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<Entry> q;
+
+  ~PyQueue() {
+    py::gil_scoped_acquire gil;
+    q.clear();
+  }
+
+  static void reply(const std::weak_ptr<RpcCore>& wc, const std::string& src, uint64_t id, const py::handle& result) {
+    auto c = wc.lock();
+    if (!c) return;
+    Writer w;
+    w.u64(id);
+    try {
+      Bytes body = pickleDumps(result);
+      w.u32(0);
+      w.str(body);
+    } catch (const std::exception& e) {
+      w.u32(1);
+      w.str(std::string("could not serialise the result: ") + e.what());
+    }
+    c->send(src, "Rpc::reply", w.b);
+  }
+
+  void push(Entry e) {
+    {
+      std::lock_guard<std::mutex> l(mu);
+      q.push_back(std::move(e));
+    }
+    cv.notify_one();
+  }
+  size_t size() {
+    std::lock_guard<std::mutex> l(mu);
+    return q.size();
+  }
+
+  // Non-blocking: None when nothing is parked.
+  py::object tryGet() {
+    std::vector<Entry> batch;
+    {
+      std::lock_guard<std::mutex> l(mu);
+      if (q.empty()) return py::none();
+      size_t n = batchSize > 0 ? std::min<size_t>((size_t)batchSize, dynamicBatching ? q.size() : (size_t)batchSize) : 1;
+      if (batchSize > 0 && !dynamicBatching && q.size() < n) return py::none();  // static batching waits for a full batch
+      for (size_t i = 0; i < n; ++i) {
+        batch.push_back(std::move(q.front()));
+        q.pop_front();
+      }
+    }
+    auto wc = core;
+    if (batchSize <= 0) {
+      Entry& e = batch[0];
+      std::string src = e.src;
+      uint64_t id = e.id;
+      py::cpp_function ret([wc, src, id](py::object result) { reply(wc, src, id, result); });
+      return py::make_tuple(ret, e.args, e.kwargs);
+    }
+    const int64_t n = (int64_t)batch.size();
+    py::tuple srcs(n);
+    std::vector<std::pair<std::string, uint64_t>> dests;
+    for (int64_t i = 0; i < n; ++i) {
+      srcs[i] = py::make_tuple(batch[i].args, batch[i].kwargs);
+      dests.emplace_back(batch[i].src, batch[i].id);
+    }
+    py::tuple stacked = py::reinterpret_borrow<py::tuple>(stackFields(srcs, 0));
+    py::cpp_function ret([wc, dests, n](py::object result) {
+      if (result.is_none()) {
+        for (auto& d : dests) reply(wc, d.first, d.second, py::none());
+        return;
+      }
+      py::tuple parts = unstackFields(result, n, 0);
+      for (int64_t i = 0; i < n; ++i) reply(wc, dests[i].first, dests[i].second, parts[i]);
+    });
+    return py::make_tuple(ret, stacked[0], stacked[1]);
+  }
+
+  py::object get(std::optional<double> timeout) {
+    auto deadline = Clock::now() + std::chrono::duration<double>(timeout ? *timeout : 1e9);
+    while (true) {
+      py::object r = tryGet();
+      if (!r.is_none()) return r;
+      if (Clock::now() >= deadline) throw std::runtime_error("Queue.get timed out");
+      {
+        py::gil_scoped_release nogil;
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait_for(l, std::chrono::milliseconds(20), [&] { return !q.empty(); });
+      }
+      if (PyErr_CheckSignals() != 0) throw py::error_already_set();
+    }
+  }
+};
+
 struct PyRpc {
   std::shared_ptr<RpcCore> core = std::make_shared<RpcCore>();
+  std::map<std::string, std::shared_ptr<PyQueue>> queues;
   std::mutex mu;
   std::map<std::string, py::object> functions;
   std::map<uint64_t, std::shared_ptr<FutureState>> calls;
@@ -514,6 +621,7 @@ struct PyRpc {
       core->close();
     }
     functions.clear();
+    queues.clear();
   }
 
   void setupServices() {
@@ -531,12 +639,24 @@ struct PyRpc {
       {
         py::gil_scoped_acquire gil;
         py::object fn;
+        std::shared_ptr<PyQueue> queue;
         {
           std::lock_guard<std::mutex> l(mu);
           auto i = functions.find(fname);
           if (i != functions.end()) fn = i->second;
+          auto qi = queues.find(fname);
+          if (qi != queues.end()) queue = qi->second;
         }
-        if (!fn) {
+        if (queue) {
+          try {
+            py::tuple ak = pickleLoads(args);
+            queue->push(PyQueue::Entry{src, id, ak[0], ak[1], Clock::now()});
+            return;  // the reply is sent when the user calls the return callback
+          } catch (const std::exception& e) {
+            w.u32(1);
+            w.str(e.what());
+          }
+        } else if (!fn) {
           w.u32(1);
           w.str("RPC function '" + fname + "' does not exist on peer '" + core->getName() + "'");
         } else {
@@ -582,6 +702,17 @@ struct PyRpc {
   void undefine(const std::string& name) {
     std::lock_guard<std::mutex> l(mu);
     functions.erase(name);
+    queues.erase(name);
+  }
+  std::shared_ptr<PyQueue> defineQueue(const std::string& name, py::kwargs kwargs) {
+    setupServices();
+    auto q = std::make_shared<PyQueue>();
+    q->core = core;
+    if (kwargs.contains("batch_size") && !kwargs["batch_size"].is_none()) q->batchSize = kwargs["batch_size"].cast<int64_t>();
+    if (kwargs.contains("dynamic_batching")) q->dynamicBatching = kwargs["dynamic_batching"].cast<bool>();
+    std::lock_guard<std::mutex> l(mu);
+    queues[name] = q;
+    return q;
   }
   std::shared_ptr<PyFuture> asyncCall(const std::string& peer, const std::string& fname, py::args args,
                                       py::kwargs kwargs) {
@@ -705,6 +836,11 @@ void bind_rpc(py::module_& m) {
       .def("wait", [](PyFuture& f, std::optional<double> t) { f.wait(t ? *t : -1.0); }, py::arg("timeout") = py::none());
   m.attr("AllReduce") = m.attr("Future");
 
+  py::class_<PyQueue, std::shared_ptr<PyQueue>>(m, "Queue")
+      .def("get", &PyQueue::get, py::arg("timeout") = py::none())
+      .def("try_get", &PyQueue::tryGet)
+      .def("size", &PyQueue::size);
+
   py::class_<PyRpc, std::shared_ptr<PyRpc>>(m, "Rpc")
       .def(py::init<>())
       .def("set_name", [](PyRpc& r, const std::string& n) { r.core->setName(n); })
@@ -716,6 +852,7 @@ void bind_rpc(py::module_& m) {
       .def("debug_info", [](PyRpc& r) { py::print(r.core->debugInfo()); })
       .def("define", [](PyRpc& r, const std::string& n, py::object fn, py::kwargs) { r.define(n, std::move(fn)); })
       .def("undefine", &PyRpc::undefine)
+      .def("define_queue", &PyRpc::defineQueue, py::arg("name"))
       .def("async_", &PyRpc::asyncCall)
       .def("sync", &PyRpc::syncCall);
 
