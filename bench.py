@@ -336,6 +336,7 @@ def run_ours(args):
             "wall_ms_per_step": round(v["wall_ms"] / K, 4),
             "frames_per_opt_step": {"value": v["frames_per_opt_step"], "e2e": e["frames_per_opt_step"],
                                     "nominal": 640 * world},
+            "optimizer_steps_per_s": {"value": round(K / (v["ms"] / 1e3), 2), "e2e": round(K / (e["ms"] / 1e3), 2)},
             "loop_stats_rank0": {"value": v["loop"], "e2e": e["loop"]},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -382,7 +383,8 @@ def reference_cuda_leg(args):
         return {"unavailable": "oracle/_ref_cuda not built"}
     out = _run_child({"MB_REF_CUDA": "1"}, ["--impl", "reference", "--gpus", "1", "--steps", str(args.steps),
                                             "--warmup", str(args.warmup), "--max-seconds", "90"], timeout=500)
-    return {k: out.get(k) for k in ("value", "unit", "ms_per_step", "e2e", "steps", "error") if k in out}
+    return {k: out.get(k) for k in ("value", "unit", "ms_per_step", "frames_per_opt_step", "optimizer_steps_per_s",
+                                    "steps", "error", "unavailable") if k in out}
 
 
 def run_reference(args):
@@ -465,6 +467,8 @@ def run_reference(args):
             "config": {"workload": "IMPALA vtrace learner loop (examples/impala.py) driven through the UNMODIFIED "
                                    f"reference moolib ({'oracle/_ref_cuda, model on cuda:0' if use_cuda else 'oracle/_ref, host cores'})",
                        "global_batch": 32 * n_peers, "parallelism": f"dp{n_peers}"},
+            "frames_per_opt_step": round(frames / max(total_steps, 1), 1),
+            "optimizer_steps_per_s": round(total_steps / n_peers / dt, 3),
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
                              "sample": sample, "aten_threads_per_peer": threads},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

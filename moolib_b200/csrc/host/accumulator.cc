@@ -31,10 +31,12 @@ struct ReduceSlot {
   std::shared_ptr<SmallReduce> reduceOp;   // CPU-parameter path
   std::vector<torch::Tensor> cpuStaging;   // CPU-parameter path (src/accumulator.cc:847-874)
   cudaEvent_t event = nullptr;             // device path: completion of the K-A2 launch
+  cudaEvent_t staged = nullptr;            // device path: the last K-A1 of this slot has run (compute stream)
   bool kernelInFlight = false;
   Clock::time_point reduceStart;
   ~ReduceSlot() {
     if (event) cudaEventDestroy(event);
+    if (staged) cudaEventDestroy(staged);
   }
 };
 
@@ -144,6 +146,7 @@ class Accumulator {
   }
 
   ~Accumulator() {
+    if (arStream_) cudaStreamDestroy(arStream_);
     parts_.rpc->unhandle("Acc::requestModel/" + resName_);
     parts_.rpc->unhandle("Acc::modelUpdate/" + resName_);
     parts_.rpc->unhandle("Acc::buffersUpdate/" + resName_);
@@ -275,6 +278,8 @@ class Accumulator {
         launch_counter() += check(mb_ar_stage(reducer()->ctx(), (int)index, ptrs.data(), numel.data(), (int)gs.size(),
                                               add ? 1 : 0, /*zero_src=*/1, current_stream(device_)),
                                   "Accumulator.reduce_gradients");
+        if (!target->staged) cudaEventCreateWithFlags(&target->staged, cudaEventDisableTiming);
+        cudaEventRecord(target->staged, c10::cuda::getCurrentCUDAStream(device_).stream());
       } else {
         if (!add) {
           target->cpuStaging.clear();
@@ -331,15 +336,27 @@ class Accumulator {
         numel.push_back((uint64_t)g.numel());
       }
       c10::cuda::CUDAGuard dg(device_);
-      auto stream = c10::cuda::getCurrentCUDAStream(device_);
+      // K-A2 runs on its own high-priority stream, ordered only after this slot's last stage kernel: it must not queue
+      // behind actor-inference work the loop has enqueued on the compute stream since then (tens of ms at 256 envs),
+      // because every peer's round waits for the slowest rank to reach its allreduce kernel.  Safe: all backward passes
+      // that contributed were followed by their stage kernel in the same reduce_gradients() call, no new backward can
+      // be enqueued once the reduce has started (wants_gradients() is false), and the compute stream is made to wait
+      // for the kernel before has_gradients() turns true.
+      if (!arStream_) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&arStream_, cudaStreamNonBlocking, hi) != cudaSuccess) arStream_ = nullptr;
+      }
+      cudaStream_t stream = arStream_ ? arStream_ : c10::cuda::getCurrentCUDAStream(device_).stream();
+      if (arStream_ && target->staged) cudaStreamWaitEvent(arStream_, target->staged, 0);
       // K-A2: barrier + P2P reduce + 1/numGradients scale + scatter into the .grad tensors, one launch
       launch_counter() += check(
           mb_ar_allreduce(reducer()->ctx(), (int)target->index, &target->data, ptrs.data(), numel.data(), (int)gs.size(),
                           nullptr, 0, /*scale=*/1, MB_AR_ALGO_AUTO, (uint32_t)(parts_.rpc->getTimeout() * 1000),
-                          static_cast<mb_stream_t>(stream.stream())),
+                          static_cast<mb_stream_t>(stream)),
           "Accumulator allreduce");
       if (!target->event) cudaEventCreateWithFlags(&target->event, cudaEventDisableTiming);
-      cudaEventRecord(target->event, stream.stream());
+      cudaEventRecord(target->event, stream);
       target->kernelInFlight = true;
     } else {
       try {
@@ -401,6 +418,8 @@ class Accumulator {
           v->reduceDone = true;  // abandon the round; the resync resets the slots
           onError();
         } else {
+          // later work on the compute stream (clip_grad_norm_, optimizer.step) is ordered after the kernel
+          cudaStreamWaitEvent(c10::cuda::getCurrentCUDAStream(device_).stream(), v->event, 0);
           finishReduce(v, total);
         }
       }
@@ -798,6 +817,7 @@ class Accumulator {
   int device_ = 0;
   std::shared_ptr<DeviceReducer> reducer_;
   bool reducerReady_ = false;
+  cudaStream_t arStream_ = nullptr;
   std::vector<std::shared_ptr<ReduceSlot>> slots_;
   size_t nextIndex_ = 0, nextResultIndex_ = 0;
   uint64_t virtualBatchSize_ = 1;
