@@ -331,7 +331,11 @@ def run_ours(args):
             "gpu_launches": int(v["launches"]),
             "roofline": {"bound": "hbm", "kernel": "copy2d_hybrid_kernel (Batcher.cat: [21,256,..] -> 8 x [21,32,..])",
                          "achieved": dom.get("achieved_gbs"), "peak": hbm, "unit": "GB/s", "frac": dom.get("frac"),
-                         "traffic": None, "peak_kind": peak_kind, "per_op": ops},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the committed ncu capture
+                         # (profiles/r01_ncu_copy_cat_152MB.md: 151.80 MB read + 98.31 MB written, the rest of the
+                         # writes is still in L2 at kernel end); algorithmic = 303.6 MB
+                         "traffic": 250105344 if args.envs == 256 else None,
+                         "peak_kind": peak_kind, "per_op": ops},
             "clocks": results.get("clocks"),
             "wall_ms_per_step": round(v["wall_ms"] / K, 4),
             "frames_per_opt_step": {"value": v["frames_per_opt_step"], "e2e": e["frames_per_opt_step"],
