@@ -178,7 +178,14 @@ class Accumulator {
   }
   bool wantsGradientsAtIndex(size_t i) {
     auto& v = slots_.at(i);
-    return !v || v->reduceDone || !v->reduceStarted;
+    if (!v || v->reduceDone) return true;
+    if (v->reduceStarted) return false;
+    // One contribution (or skip) per count round.  The reference keeps asking for gradients while a count is in flight
+    // (src/accumulator.cc:398-404, 984-988 wantsMoreCounting), so a fast loop squeezes extra batches into every
+    // reduction and the virtual batch size overshoots (measured: 2.7x at 8 peers).  Holding back until the count returns
+    // keeps reductions at the configured size; MOOLIB_B200_STRICT_COUNTING=0 restores the reference behaviour.
+    if (strictCounting_ && v->isCounting) return false;
+    return true;
   }
   bool wantsGradientsLocked() {
     return connectedImpl() && wantsGradientsAtIndex(nextIndex_) && !isWaitingForModel_ && !isFindingLeader_ &&
@@ -818,6 +825,10 @@ class Accumulator {
   std::shared_ptr<DeviceReducer> reducer_;
   bool reducerReady_ = false;
   cudaStream_t arStream_ = nullptr;
+  bool strictCounting_ = [] {
+    const char* e = std::getenv("MOOLIB_B200_STRICT_COUNTING");
+    return !(e && *e == '0');
+  }();
   std::vector<std::shared_ptr<ReduceSlot>> slots_;
   size_t nextIndex_ = 0, nextResultIndex_ = 0;
   uint64_t virtualBatchSize_ = 1;
