@@ -393,9 +393,9 @@ def reference_cuda_leg(args):
 
 def run_reference(args):
     rank, local, world = dist_env()
-    if rank != 0:
-        return
     use_cuda = os.environ.get("MB_REF_CUDA") == "1"
+    if rank != 0 and not use_cuda:
+        return
     ref_dir = os.path.join(ROOT, "oracle", "_ref_cuda" if use_cuda else "_ref")
     import torch
     sys.path.insert(0, ref_dir)
@@ -406,26 +406,39 @@ def run_reference(args):
         return
     from examples import impala
 
-    n_peers = max(world, args.gpus) if not use_cuda else 1
-    device = "cuda:0" if use_cuda else "cpu"
+    # MB_REF_CUDA=1 (information only, not the driver's reference arm): the reference compiled with -DUSE_CUDA, one
+    # process per GPU under torchrun exactly like our arm, models on the GPUs, ITS OWN RPC transport between the processes.
+    multi = use_cuda and world > 1
+    if multi:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("gloo")
+    n_peers = 1 if use_cuda else max(world, args.gpus)
+    device = f"cuda:{local}" if use_cuda else "cpu"
     cores = os.cpu_count()
     # ATen's CPU kernels stop scaling (and start thrashing) far below the core count of a 128-core host for these
     # small convolutions; the reference's own scheduler also takes min(cores-1, 64) threads (src/async.cc:67-83)
-    threads = max(1, min(cores, 32) // n_peers)
+    threads = max(1, min(cores, 32) // max(n_peers, world if multi else 1))
     torch.set_num_threads(threads)
     K, W = args.steps, args.warmup
-    port = 29400 + 57 + (os.getpid() % 500)
+    if multi:
+        port = int(os.environ.get("MASTER_PORT", 29400)) + 41
+    else:
+        port = 29400 + 57 + (os.getpid() % 500)
     addr = f"127.0.0.1:{port}"
-    broker = ref.Broker()
-    broker.listen(addr)
+    broker = None
+    if rank == 0:
+        broker = ref.Broker()
+        broker.listen(addr)
+    total_peers = world if multi else n_peers
     loops = []
-    # N reference peers share ONE host process here (rank 0 only runs this arm): bound the sample by shrinking the actor
-    # pool per peer -- the learner batch (T=21 x 32) and the reduction (N peers, 4.38 MB) are the full-size ones.
-    envs_per_peer = args.envs if n_peers == 1 else max(32, args.envs // n_peers)
+    # N reference peers share ONE host process in the CPU arm (rank 0 only runs it): bound the sample by shrinking the
+    # actor pool per peer -- the learner batch (T=21 x 32) and the reduction (N peers, 4.38 MB) are the full-size ones.
+    envs_per_peer = args.envs if (n_peers == 1) else max(32, args.envs // n_peers)
     for i in range(n_peers):
-        flags = impala.Flags(actor_batch_size=envs_per_peer, virtual_batch_size=32 * n_peers, device=device,
+        flags = impala.Flags(actor_batch_size=envs_per_peer, virtual_batch_size=32 * total_peers, device=device,
                              host_obs=True, read_metrics=True)
-        flags.seed += i
+        flags.seed += i + rank
         model, opt = impala.make_learner(flags)
         acc = ref.Accumulator("impala", model.parameters(), model.buffers())
         acc.set_virtual_batch_size(flags.virtual_batch_size)
@@ -457,26 +470,40 @@ def run_reference(args):
             break
     sync()
     if t0 is None or sum(lp.res.env_train_steps - b for lp, b in zip(loops, base_frames)) == 0:
-        print(json.dumps({"impl": "reference", "unavailable": "no gradient batch completed within --max-seconds"}))
-        return
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "no gradient batch completed within --max-seconds"}))
+        os._exit(0)
     dt = time.perf_counter() - t0
     total_steps = sum(lp.res.optimizer_steps - b for lp, b in zip(loops, base))
     frames = sum(lp.res.env_train_steps - b for lp, b in zip(loops, base_frames))  # experiment.py:155
+    if multi:
+        t = torch.tensor([float(frames), float(total_steps), dt], dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        frames, total_steps, dt = t[0].item(), t[1].item(), tmax[2].item()
+        # keep serving the peers until everybody has its numbers
+        w = dist.barrier(async_op=True)
+        while not w.is_completed():
+            for lp in loops:
+                lp.tick()
     value = frames / dt
-    sample = (f"{done_steps} of {K} optimizer steps per peer x {n_peers} peer(s) in one process, device={device}, "
+    sample = (f"{done_steps} of {K} optimizer steps per peer x {total_peers} peer(s)"
+              f"{' (one process per GPU)' if multi else ' in one process'}, device={device}, "
               f"{envs_per_peer} envs per peer, T=21, batch 32 per peer, {dt:.1f} s")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
             "steps": done_steps, "warmup": W, "ms_per_step": round(dt * 1e3 / max(done_steps, 1), 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "IMPALA vtrace learner loop (examples/impala.py) driven through the UNMODIFIED "
-                                   f"reference moolib ({'oracle/_ref_cuda, model on cuda:0' if use_cuda else 'oracle/_ref, host cores'})",
-                       "global_batch": 32 * n_peers, "parallelism": f"dp{n_peers}"},
-            "frames_per_opt_step": round(frames / max(total_steps, 1), 1),
-            "optimizer_steps_per_s": round(total_steps / n_peers / dt, 3),
+                                   f"reference moolib ({'oracle/_ref_cuda, models on the GPUs' if use_cuda else 'oracle/_ref, host cores'})",
+                       "global_batch": 32 * total_peers, "parallelism": f"dp{total_peers}"},
+            "frames_per_opt_step": round(frames / max(total_steps / total_peers, 1), 1),
+            "optimizer_steps_per_s": round(total_steps / total_peers / dt, 3),
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "reference",
                              "sample": sample, "aten_threads_per_peer": threads},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     os._exit(0)  # the reference's RPC threads do not always join cleanly at interpreter exit
 
 
