@@ -9,5 +9,5 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:copy
   python tools/sweep_copy.py --envs 256 --reps 2 --warmup 1 --out gpurun_out/ncu_dummy.json > gpurun_out/ncu_hybrid.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:ar_ -s 4 -c 4 -o gpurun_out/prof_allreduce_w1 -f \
   python bench.py --steps 3 --warmup 2 --no-cpu-baseline --ref-cuda 0 > gpurun_out/ncu_ar.log 2>&1
-timeout 300 python -m pytest tests/test_envpool_gpu.py -m gpu -x -q 2>&1 | tail -5
+timeout 300 python -m pytest tests/test_env_workers_gpu.py -m gpu -x -q 2>&1 | tail -5
 ls -la gpurun_out | tail -12
