@@ -463,6 +463,17 @@ int launch_chunk(const mb_copy_job* jobs, int n, cudaStream_t stream) {
       j.rows = 1;
     }
     bulk[nj] = tn.impl != kImplLdg && job_tma_ok(j);
+    if (bulk[nj]) {
+      // Host-mapped sources (pinned EnvPool slabs) stay on the LDG path, which is the one validated for zero-copy
+      // reads over PCIe; the bulk-async path is for device-resident sources.
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, j.src) != cudaSuccess) {
+        cudaGetLastError();
+        bulk[nj] = false;
+      } else if (attr.type != cudaMemoryTypeDevice) {
+        bulk[nj] = false;
+      }
+    }
     if (bulk[nj]) bulk_bytes += j.rows * j.row_bytes;
     norm[nj++] = j;
   }

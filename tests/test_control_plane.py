@@ -290,3 +290,92 @@ def test_recount_after_failed_count_does_not_deadlock():
                 a.zero_gradients()
                 rounds += 1
         assert time.time() - t0 < 90
+
+
+def _drive(c, models, accs, rounds, value_fn, max_s=90, extra_pump=()):
+    """Standard loop: contribute when asked, apply when available; returns the list of applied gradients per peer."""
+    seen = [[] for _ in accs]
+    t0 = time.time()
+    while min(len(s) for s in seen) < rounds:
+        c.pump(list(accs) + list(extra_pump))
+        for i, (m, a) in enumerate(zip(models, accs)):
+            if a.wants_state():
+                a.set_state({"k": i})
+            if a.has_new_state():
+                a.state()
+            if a.has_gradients():
+                seen[i].append((m.weight.grad.flatten()[0].item(), a.get_gradient_stats()["num_gradients"]))
+                a.zero_gradients()
+            elif a.wants_gradients():
+                v = value_fn(i, len(seen[i]))
+                m.weight.grad = torch.full_like(m.weight, v)
+                m.bias.grad = torch.full_like(m.bias, v)
+                a.reduce_gradients(1)
+        assert time.time() - t0 < max_s, [len(s) for s in seen]
+    return seen
+
+
+@pytest.mark.timeout(180)
+def test_parallel_gradients_ring():
+    """set_parallel_gradients(2): two reduction slots used round-robin (src/accumulator.cc:889-903); every applied
+    gradient is the average of one contribution per peer, identical on both peers, in order."""
+    c = Cluster(2, group="ring")
+    c.form()
+    models, accs = _make_accumulators(c, 2, 2)
+    for a in accs:
+        a.set_parallel_gradients(2)
+        a.set_virtual_batch_size(2)
+    seen = _drive(c, models, accs, 12, lambda i, k: float(i + 1))
+    for s in seen:
+        assert all(abs(v - 1.5) < 1e-6 and ng == 2 for v, ng in s[:12]), s
+    with pytest.raises(RuntimeError):
+        accs[0].set_parallel_gradients(9)
+
+
+@pytest.mark.timeout(240)
+def test_training_survives_a_peer_joining_and_leaving():
+    """Elasticity: a third peer joins mid-run (new syncId -> reductions reset, leader re-elected,
+    model pushed to the joiner), later leaves (times out at the broker) and the remaining two carry on."""
+    c = Cluster(2, group="elastic")
+    c.form()
+    models, accs = _make_accumulators(c, 2, 2)
+    seen = _drive(c, models, accs, 5, lambda i, k: 1.0)
+    assert all(abs(v - 1.0) < 1e-6 for s in seen for v, _ in s)
+    # make the incumbents' parameters distinctive so that we can see the joiner receive them
+    with torch.no_grad():
+        for m in models:
+            m.weight.fill_(0.25)
+            m.bias.fill_(-0.5)
+    for a in accs:
+        a.set_model_version(100)
+    r = moolib.Rpc()
+    r.set_name("peer2")
+    r.set_timeout(20)
+    r.connect(c.addr)
+    g = moolib.Group(r, "elastic")
+    g.set_timeout(2.0)
+    g.set_sort_order(2)
+    m3 = torch.nn.Linear(32, 31)
+    a3 = moolib.Accumulator("acc", m3.parameters(), m3.buffers(), group=g)
+    a3.set_virtual_batch_size(3)
+    for a in accs:
+        a.set_virtual_batch_size(3)
+    c.rpcs.append(r)
+    c.groups.append(g)
+    seen = _drive(c, models + [m3], accs + [a3], 5, lambda i, k: float(i + 1))
+    assert torch.equal(m3.weight, models[0].weight) and torch.equal(m3.bias, models[0].bias)  # model sync to the joiner
+    assert a3.model_version() >= 100
+    assert all(abs(v - 2.0) < 1e-6 for v, ng in seen[2][-2:])  # (1+2+3)/3 once all three contribute
+    # the joiner disappears
+    c.groups.pop()
+    c.rpcs.pop()
+    del a3, g, r
+    for a in accs:
+        a.set_virtual_batch_size(2)
+    t0 = time.time()
+    while len(c.groups[0].members()) != 2:
+        c.pump(accs)
+        time.sleep(0.01)
+        assert time.time() - t0 < 60
+    seen = _drive(c, models, accs, 3, lambda i, k: 4.0)
+    assert all(abs(v - 4.0) < 1e-6 for s in seen for v, _ in s[-2:])
