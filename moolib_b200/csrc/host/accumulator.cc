@@ -147,9 +147,8 @@ class Accumulator {
 
   ~Accumulator() {
     if (arStream_) cudaStreamDestroy(arStream_);
-    parts_.rpc->unhandle("Acc::requestModel/" + resName_);
-    parts_.rpc->unhandle("Acc::modelUpdate/" + resName_);
-    parts_.rpc->unhandle("Acc::buffersUpdate/" + resName_);
+    unhandleAll(*parts_.rpc, {"Acc::requestModel/" + resName_, "Acc::modelUpdate/" + resName_,
+                              "Acc::buffersUpdate/" + resName_});
   }
 
   void connect(const std::string& address) { parts_.rpc->connect(address); }

@@ -51,6 +51,18 @@ torch::Tensor unpackTensor(const std::string& b);
 std::string pickleDumps(const py::handle& o);
 py::object pickleLoads(const std::string& b);
 
+// Unregister control-plane handlers from a destructor that may run with the GIL held: a handler that is executing on
+// the IO thread may itself be waiting for the GIL (Python reduce ops, Rpc::call), and unhandle() waits for it.
+template <typename Rpc>
+void unhandleAll(Rpc& rpc, std::initializer_list<std::string> names) {
+  if (PyGILState_Check()) {
+    py::gil_scoped_release nogil;
+    for (auto& n : names) rpc.unhandle(n);
+  } else {
+    for (auto& n : names) rpc.unhandle(n);
+  }
+}
+
 // utils::stackFields / unstackFields (reference: src/batch_utils.cc:259-325), implemented in batcher.cc
 py::object stackFields(const py::tuple& input, int64_t dim);
 py::tuple unstackFields(const py::handle& input, int64_t batchSize, int64_t dim);

@@ -22,6 +22,7 @@
 #include <mutex>
 #include <optional>
 #include <set>
+#include <shared_mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -131,7 +132,9 @@ class RpcCore : public std::enable_shared_from_this<RpcCore> {
   };
   std::deque<Parked> parked_;
   std::deque<Parked> outbox_;  // client side: sends issued before connect() completed
-  std::mutex hmu_;
+  // Handlers run under a shared lock; handle()/unhandle() take it exclusively, so once unhandle() returns no call of
+  // that handler is still executing (services unregister in their destructors).
+  std::shared_mutex hmu_;
   std::unordered_map<std::string, Handler> handlers_;
   std::thread thread_;
   bool threadStarted_ = false;

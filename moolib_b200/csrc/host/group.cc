@@ -88,7 +88,7 @@ GroupService::GroupService(std::shared_ptr<RpcCore> rpc) : rpc_(std::move(rpc)) 
 }
 
 GroupService::~GroupService() {
-  for (const char* s : {"Group::pong", "Group::sync", "Group::update", "AR::contrib", "AR::result"}) rpc_->unhandle(s);
+  unhandleAll(*rpc_, {"Group::pong", "Group::sync", "Group::update", "AR::contrib", "AR::result"});
 }
 
 std::shared_ptr<GroupInfo> GroupService::group(const std::string& name) {
@@ -374,9 +374,7 @@ BrokerService::BrokerService(std::shared_ptr<RpcCore> rpc) : rpc_(std::move(rpc)
   });
 }
 
-BrokerService::~BrokerService() {
-  for (const char* s : {"Broker::ping", "Broker::resync", "Broker::syncReply"}) rpc_->unhandle(s);
-}
+BrokerService::~BrokerService() { unhandleAll(*rpc_, {"Broker::ping", "Broker::resync", "Broker::syncReply"}); }
 
 void BrokerService::update() {
   MBH_PHASE("BrokerService::update");
@@ -614,8 +612,7 @@ struct PyRpc {
   bool servicesUp = false;
 
   ~PyRpc() {
-    core->unhandle("Rpc::call");
-    core->unhandle("Rpc::reply");
+    unhandleAll(*core, {"Rpc::call", "Rpc::reply"});
     {
       py::gil_scoped_release nogil;
       core->close();
@@ -792,7 +789,11 @@ struct PyGroup {
     if (kwargs.contains("op")) op = kwargs["op"];
     auto fut = std::make_shared<PyFuture>();
     if (!op.is_none()) {
-      auto pop = std::make_shared<py::object>(op);
+      // the callable may be released from the IO thread: its reference must be dropped under the GIL
+      std::shared_ptr<py::object> pop(new py::object(op), [](py::object* o) {
+        py::gil_scoped_acquire gil;
+        delete o;
+      });
       auto red = service->allReduce(info, name, pickleDumps(data), [pop](const Bytes& a, const Bytes& b) {
         py::gil_scoped_acquire gil;
         return pickleDumps((*pop)(pickleLoads(a), pickleLoads(b)));

@@ -206,12 +206,12 @@ void RpcCore::connect(const std::string& address) {
 }
 
 void RpcCore::handle(const std::string& service, Handler h) {
-  std::lock_guard<std::mutex> l(hmu_);
+  std::unique_lock<std::shared_mutex> l(hmu_);
   handlers_[service] = std::move(h);
 }
 
 void RpcCore::unhandle(const std::string& service) {
-  std::lock_guard<std::mutex> l(hmu_);
+  std::unique_lock<std::shared_mutex> l(hmu_);
   handlers_.erase(service);
 }
 
@@ -261,16 +261,12 @@ void RpcCore::send(const std::string& dst, const std::string& service, const Byt
 }
 
 void RpcCore::deliverLocal(const std::string& src, const std::string& service, const Bytes& payload) {
-  Handler h;
-  {
-    std::lock_guard<std::mutex> l(hmu_);
-    auto i = handlers_.find(service);
-    if (i == handlers_.end()) return;
-    h = i->second;
-  }
+  std::shared_lock<std::shared_mutex> l(hmu_);  // held while the handler runs (see control.h)
+  auto i = handlers_.find(service);
+  if (i == handlers_.end()) return;
   ++received_;
   try {
-    h(src, payload);
+    i->second(src, payload);
   } catch (const std::exception&) {
     // a malformed control message must not take the IO thread down
   }
