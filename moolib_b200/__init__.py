@@ -9,7 +9,7 @@ import os as _os
 
 _here = _os.path.dirname(_os.path.abspath(__file__))
 if not _os.path.exists(_os.path.join(_here, "lib", "libmoolib_b200.so")):
-    raise ImportError("moolib_b200/lib/libmoolib_b200.so is missing; build it with `python -m moolib_b200.build`")
+    raise ImportError("moolib_b200/lib/libmoolib_b200.so is missing; build it with `python moolib_b200/build.py`")
 
 import torch as _torch  # noqa: E402,F401  (libtorch must be loaded before the extension)
 
@@ -18,7 +18,7 @@ try:
 except ImportError as e:  # pragma: no cover
     raise ImportError(
         "moolib_b200._C (the compiled host layer) is missing or failed to load; build it with "
-        "`python -m moolib_b200.build`") from e
+        "`python moolib_b200/build.py`") from e
 
 from ._C import Batcher  # noqa: E402,F401
 

@@ -58,7 +58,7 @@ def load():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m moolib_b200.build` (nvcc, sm_100a). "
+            f"{LIB_PATH} is missing: build it with `python moolib_b200/build.py` (nvcc, sm_100a). "
             "There is no CPU fallback for the moolib_b200 hot paths.")
     L = ctypes.CDLL(LIB_PATH)
     vp, u64, i64, ci, u32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int, ctypes.c_uint32

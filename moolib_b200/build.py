@@ -3,7 +3,7 @@
   libmoolib_b200.so   CUDA kernels + C-ABI (include/moolib_b200.h), nvcc, sm_100a only
   _C*.so              pybind11 host layer mirroring moolib's Python API (moolib_b200/csrc/host), g++ over libtorch
 
-`python -m moolib_b200.build [--force] [--only lib|host]`
+`python moolib_b200/build.py [--force] [--only lib|host]`
 """
 import os
 import subprocess
