@@ -160,3 +160,49 @@ def test_oracle_batcher_matches_live_reference():
                 assert a.empty() == b.empty()
                 while not a.empty():
                     assert a.get().equal(b.get())
+
+
+@pytest.mark.skipif(not oracle.reference_available(), reason="oracle/_ref not built in this checkout")
+@pytest.mark.timeout(180)
+def test_oracle_tree_allreduce_matches_live_reference():
+    """group.all_reduce of the compiled reference, run live with N in-process peers (test/test_reduce.py layout), equals
+    the C restatement of the tree for one of the legal arrival orders -- bit for bit, fresh random inputs."""
+    import time
+    moolib = oracle.load_reference()
+    n = 4
+    addr = "127.0.0.1:4871"
+    broker_rpc = moolib.Rpc()
+    broker_rpc.set_name("broker")
+    broker = moolib.Broker(broker_rpc)
+    broker_rpc.listen(addr)
+    rpcs, groups = [], []
+    for i in range(n):
+        r = moolib.Rpc()
+        r.set_name(f"peer{i}")
+        r.set_timeout(30)
+        r.connect(addr)
+        g = moolib.Group(r, "live")
+        g.set_timeout(30)
+        g.set_sort_order(i)
+        rpcs.append(r)
+        groups.append(g)
+    t0 = time.time()
+    while not (all(g.active() and len(g.members()) == n for g in groups) and len({g.sync_id() for g in groups}) == 1):
+        broker.update()
+        for g in groups:
+            g.update()
+        time.sleep(0.02)
+        assert time.time() - t0 < 90
+    rng = np.random.default_rng(2026)
+    for rep in range(3):
+        ins = [rng.standard_normal(2049).astype(np.float32) for _ in range(n)]
+        futs = [groups[r].all_reduce(f"live{rep}", torch.from_numpy(ins[r].copy())) for r in range(n)]
+        res = [f.result(30).numpy() for f in futs]
+        assert all(r.tobytes() == res[0].tobytes() for r in res)
+        assert any(oracle.allreduce_tree(ins, [(1, 0, 1)] * n, order=m, scale=False)[0].tobytes() == res[0].tobytes()
+                   for m in tree_masks(n))
+        ours, _ = oracle.allreduce_rankorder(ins, [(1, 0, 1)] * n, scale=False)
+        assert (np.abs(ours.astype(np.float64) - res[0]) <= oracle.allreduce_tolerance(ins, res[0])).all()
+        broker.update()
+        for g in groups:
+            g.update()
