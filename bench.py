@@ -371,8 +371,8 @@ def _run_child(extra_env, argv, timeout):
 
 def cpu_baseline_leg(args):
     """The reference's own CPU path (oracle/_ref) on this box's host cores, bounded sample of the same workload."""
-    out = _run_child({}, ["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "0", "--max-seconds", "150"],
-                     timeout=600)
+    out = _run_child({}, ["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "0", "--max-seconds", "75"],
+                     timeout=300)
     if "cpu_baseline" in out:
         return out["cpu_baseline"]
     return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed",
@@ -385,8 +385,8 @@ def reference_cuda_leg(args):
     through pinned host memory and reduces on the CPU)."""
     if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref_cuda", "moolib")):
         return {"unavailable": "oracle/_ref_cuda not built"}
-    out = _run_child({"MB_REF_CUDA": "1"}, ["--impl", "reference", "--gpus", "1", "--steps", str(args.steps),
-                                            "--warmup", str(args.warmup), "--max-seconds", "90"], timeout=500)
+    out = _run_child({"MB_REF_CUDA": "1"}, ["--impl", "reference", "--gpus", "1", "--steps", str(min(args.steps, 40)),
+                                            "--warmup", str(min(args.warmup, 8)), "--max-seconds", "60"], timeout=300)
     return {k: out.get(k) for k in ("value", "unit", "ms_per_step", "frames_per_opt_step", "optimizer_steps_per_s",
                                     "steps", "error", "unavailable") if k in out}
 
