@@ -82,3 +82,31 @@ def test_env_exception_is_reported():
     envs.step(0, torch.zeros(4).long()).result()
     with pytest.raises(RuntimeError, match="Error in env"):
         envs.step(0, torch.full((4,), 9).long()).result()  # ToyEnv raises on action 9
+
+
+@pytest.mark.timeout(300)
+def test_envpool_feeds_batcher_like_the_vtrace_loop():
+    """EnvPool -> time Batcher -> learn Batcher on CPU: the data path of examples/vtrace/experiment.py:489-523 with real
+    worker processes; the batches equal torch.stack / narrow of what the envs produced."""
+    B, T, Bl = 6, 4, 3
+    envs = moolib.EnvPool(FrameEnv, batch_size=B, num_batches=1, num_processes=2)
+    tb = moolib.Batcher(T, "cpu")
+    lb = moolib.Batcher(Bl, "cpu", dim=1)
+    rng = np.random.Generator(np.random.PCG64(5))
+    seen = []
+    action = torch.zeros(B, dtype=torch.int64)
+    for t in range(T):
+        obs = envs.step(0, action).result()
+        step = {k: v.clone() for k, v in obs.items()}  # result() aliases the slab until the next step()
+        seen.append(step)
+        tb.stack(step)
+        action = torch.from_numpy(rng.integers(0, 18, size=B, dtype=np.int64))
+    data = tb.get()
+    for k in ("state", "reward", "done"):
+        assert data[k].equal(torch.stack([s[k] for s in seen]))
+    lb.cat(data)
+    assert lb.size() == B // Bl
+    for i in range(B // Bl):
+        mb = lb.get()
+        assert mb["state"].shape == (T, Bl, 4, 84, 84)
+        assert mb["state"].equal(data["state"][:, i * Bl:(i + 1) * Bl])
