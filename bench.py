@@ -146,8 +146,15 @@ class BatchOpTimer:
                 continue
             alg = 2 * d["payload"]  # read every source byte once + write every destination byte once
             out[op] = {"launches": d["launches"], "avg_launch_us": round(d["ms"] * 1e3 / d["launches"], 3),
-                       "alg_bytes_per_launch": alg // d["launches"], "achieved_gbs": round(alg / d["ms"] / 1e6, 1),
+                       "total_ms": round(d["ms"], 4), "alg_bytes_per_launch": alg // d["launches"],
+                       "alg_bytes_total": alg, "achieved_gbs": round(alg / d["ms"] / 1e6, 1),
                        "frac": round(alg / d["ms"] / 1e6 / hbm_gbs, 4)}
+        if out:
+            tot_ms = sum(o["total_ms"] for o in out.values())
+            tot_b = sum(o["alg_bytes_total"] for o in out.values())
+            out["_all"] = {"launches": sum(o["launches"] for o in out.values()), "total_ms": round(tot_ms, 4),
+                           "alg_bytes_total": tot_b, "achieved_gbs": round(tot_b / tot_ms / 1e6, 1),
+                           "frac": round(tot_b / tot_ms / 1e6 / hbm_gbs, 4)}
         return out
 
 
@@ -157,6 +164,98 @@ def measured_peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(q * len(xs)))] if xs else None
+
+
+def parity_rounds(acc, model, pump, rank, world, torch, dist):
+    """Two CHECKED reductions through the public Accumulator on the real 36-tensor gradient layout, before any timed
+    region (reference semantics: src/group.h:570-654 tree sum, src/accumulator.cc:433-452 x 1.0f/numGradients; the
+    reference's own check is test/test_reduce.py:66-81).  Round A: rank r contributes r+1 everywhere.  Round B:
+    randn(seed=r).  Every rank compares its result bit for bit with the CPU oracle in the kernel's summation order
+    (oracle = checker only) and the CRCs of all ranks must agree."""
+    import zlib
+
+    import numpy as np
+
+    import oracle
+
+    params = [p for p in model.parameters() if p.requires_grad]
+    numels = [p.numel() for p in params]
+    offs, total = oracle.flat_layout(numels)
+    out = {"n": world, "rounds": [], "exact": True, "tensors": len(params), "floats": int(sum(numels))}
+
+    def inputs_of(kind, q):
+        f = np.zeros(total, dtype=np.float32)
+        if kind == "rank+1":
+            for o, n in zip(offs, numels):
+                f[o:o + n] = float(q + 1)
+        else:
+            g = torch.Generator().manual_seed(7700 + q)
+            for o, n in zip(offs, numels):
+                f[o:o + n] = torch.randn(n, generator=g).numpy()
+        return f
+
+    for kind in ("rank+1", "randn"):
+        t0 = time.time()
+        while not acc.wants_gradients():
+            pump()
+            if time.time() - t0 > 120:
+                raise RuntimeError(f"rank {rank}: parity round {kind}: accumulator never asked for gradients")
+        mine = inputs_of(kind, rank)
+        with torch.no_grad():
+            for p, o, n in zip(params, offs, numels):
+                p.grad.copy_(torch.from_numpy(mine[o:o + n]).view_as(p))  # in place: .grad lives in the NVLink staging
+        acc.reduce_gradients(32)
+        t0 = time.time()
+        while not acc.has_gradients():
+            pump()
+            if time.time() - t0 > 120:
+                raise RuntimeError(f"rank {rank}: parity round {kind}: no result")
+        got = np.zeros(total, dtype=np.float32)
+        for p, o, n in zip(params, offs, numels):
+            got[o:o + n] = p.grad.detach().reshape(-1).cpu().numpy()
+        exact, eh = oracle.allreduce_rankorder([inputs_of(kind, q) for q in range(world)], [(1, 0, 32)] * world)
+        ok = got.tobytes() == exact.tobytes()
+        stats = acc.get_gradient_stats()
+        ok = ok and (stats["num_gradients"], stats["num_skipped"], stats["batch_size"]) == tuple(eh[:3])
+        crc = zlib.crc32(got.tobytes())
+        crcs = [crc]
+        if world > 1:
+            crcs = [None] * world
+            dist.all_gather_object(crcs, crc)
+            oks = [None] * world
+            dist.all_gather_object(oks, bool(ok))
+            ok = all(oks)
+        same = len(set(crcs)) == 1
+        out["rounds"].append({"input": kind, "bit_exact_vs_oracle_all_ranks": bool(ok), "identical_on_all_ranks": same,
+                              "crc32": f"{crcs[0]:08x}", "max_abs": float(np.abs(got).max())})
+        out["exact"] = out["exact"] and bool(ok) and same
+        acc.zero_gradients()
+    return out
+
+
+def nvlink_roofline(tm, world):
+    """K-A2 inside the timed region, from the Accumulator's own CUDA events on its reduce stream."""
+    red = [t for t, ok in zip(tm["reduce_us"], tm["reduced"]) if ok]
+    gate = [t for t, ok in zip(tm["gate_us"], tm["reduced"]) if ok]
+    if not red:
+        return None
+    S = tm["bytes"]
+    avg = sum(red) / len(red)
+    two = world > 2 and S >= ((4 << 20) if world <= 4 else (1 << 20))
+    busbw = S * 2 * (world - 1) / world / avg / 1e3 if world > 1 else 0.0  # GB/s
+    ingress = (S * 2 * (world - 1) / world if two else S * (world - 1)) / avg / 1e3
+    return {"kernel": ("ar_twoshot_kernel" if two else "ar_oneshot_kernel") + f"<{world}>", "algo": "twoshot" if two else "oneshot",
+            "bytes": S, "rounds": len(red), "avg_us": round(avg, 2), "p50_us": round(_pct(red, 0.5), 2),
+            "p90_us": round(_pct(red, 0.9), 2), "gate_wait_p50_us": round(_pct(gate, 0.5), 2),
+            "gate_wait_p90_us": round(_pct(gate, 0.9), 2), "busbw_gbs": round(busbw, 1),
+            "ingress_gbs": round(ingress, 1), "peak": 770.0, "peak_kind": "B200_PROFILING.md measured peer copy per direction",
+            "frac_of_770": round(ingress / 770.0, 4), "short_rounds": tm["short_rounds"],
+            "stage_launches": tm["stage_launches"], "zero_copy_rounds": tm["zero_copy_rounds"]}
 
 
 def run_ours(args):
@@ -230,6 +329,12 @@ def run_ours(args):
         barrier()
 
     wait_for_full_group()
+    parity = parity_rounds(acc, model, pump, rank, world, torch, dist)
+    if not parity["exact"]:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "error": "allreduce parity check failed", "parity": parity}), flush=True)
+        sys.exit(3)
+    barrier()
 
     def dbg(msg):
         if os.environ.get("BENCH_DEBUG"):
@@ -260,15 +365,21 @@ def run_ours(args):
                 state["frames0"] = res.env_train_steps
                 state["stats0"] = (res.t_learn, res.t_act, res.t_opt, res.t_idle, res.n_learn, res.n_skip, res.n_idle)
                 timer.enabled = mode == "value"
+                acc.reduce_timings(clear=True)
                 state["t0"] = time.perf_counter()
+                state["step_t"] = [state["t0"]]
                 start_evt.record()
                 return True
+            if state.get("t0") is not None and n < W + K:
+                state["step_t"].append(time.perf_counter())
             if n == W + K:
                 end_evt.record()
                 dbg(f"{mode}: end recorded, synchronizing")
                 torch.cuda.synchronize()
                 dbg(f"{mode}: synchronized")
                 state["t1"] = time.perf_counter()
+                state["step_t"].append(state["t1"])
+                state["ar"] = acc.reduce_timings()
                 state["launches"] = _C.kernel_launches() - state["launch0"]
                 state["actor_steps"] = res.actor_steps - state["actor0"]
                 state["frames"] = res.env_train_steps - state["frames0"]
@@ -288,9 +399,15 @@ def run_ours(args):
         wall = (state["t1"] - state["t0"]) * 1e3
         t = torch.tensor([ms, wall], dtype=torch.float64)
         fr = torch.tensor([float(state["frames"])], dtype=torch.float64)
+        slowest = rank
         if world > 1:
+            all_ms = [None] * world
+            dist.all_gather_object(all_ms, float(ms))
+            slowest = max(range(world), key=lambda i: all_ms[i])
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+        st = state["step_t"]
+        step_ms = [(b - a) * 1e3 for a, b in zip(st, st[1:])]
         # frames = the reference's env_train_steps (examples/vtrace/experiment.py:155): unroll_length * batch_size per
         # gradient batch computed, summed over all learners.  With virtual_batch_size == batch_size * N it equals
         # unroll_length * batch_size * N * optimizer_steps whenever every learner contributes exactly once per round.
@@ -299,7 +416,9 @@ def run_ours(args):
                          "frames_per_opt_step": frames / max(K, 1), "loop": state["loop"],
                          "value": frames / (t[0].item() / 1e3), "launches": state["launches"],
                          "actor_steps": state["actor_steps"], "loss": float(res.last_loss),
-                         "h2d": envs.h2d_bytes, "d2h": envs.d2h_bytes}
+                         "h2d": envs.h2d_bytes, "d2h": envs.d2h_bytes, "ar": state["ar"], "slowest_rank": slowest,
+                         "step_ms": {"p50": round(_pct(step_ms, 0.5), 3), "p90": round(_pct(step_ms, 0.9), 3),
+                                     "max": round(max(step_ms), 3), "clock": "host wall between optimizer steps, rank 0"}}
         if sampler:
             results["clocks"] = sampler.stop()
         # let the peers drain before the next mode
@@ -313,7 +432,10 @@ def run_ours(args):
     if rank == 0:
         v, e = results["value"], results["e2e"]
         ops = timer.summary(hbm, peak_kind)
-        dom = ops.get("cat") or ops.get("stack") or {}
+        # the dominant moolib_b200 kernel family = the Batcher op with the most device time inside the timed region
+        named = {k: o for k, o in ops.items() if not k.startswith("_")}
+        dom_name = max(named, key=lambda k: named[k]["total_ms"]) if named else None
+        dom = named.get(dom_name, {})
         # H2D per optimizer step: actor steps per optimizer step x one [B] observation slab; D2H: the grad-norm read
         actor_per_step = e["actor_steps"] / max(K, 1)
         line = {
@@ -329,13 +451,14 @@ def run_ours(args):
             "e2e": {"value": round(e["value"], 1), "unit": UNIT, "ms_per_step": round(e["ms"] / K, 4),
                     "h2d_bytes_per_step": int(actor_per_step * e["h2d"]), "d2h_bytes_per_step": 4},
             "gpu_launches": int(v["launches"]),
-            "roofline": {"bound": "hbm", "kernel": "copy2d_hybrid_kernel (Batcher.cat: [21,256,..] -> 8 x [21,32,..])",
+            "roofline": {"bound": "hbm", "kernel": f"Batcher.{dom_name} (dominant moolib_b200 op by device time in the step)",
                          "achieved": dom.get("achieved_gbs"), "peak": hbm, "unit": "GB/s", "frac": dom.get("frac"),
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the committed ncu capture
-                         # (profiles/r01_ncu_copy_cat_152MB.md: 151.80 MB read + 98.31 MB written, the rest of the
-                         # writes is still in L2 at kernel end); algorithmic = 303.6 MB
-                         "traffic": 250105344 if args.envs == 256 else None,
-                         "peak_kind": peak_kind, "per_op": ops},
+                         "traffic": None,  # not measured in this run; see profiles/ for the ncu --set full capture
+                         "peak_kind": peak_kind, "per_op": ops, "aggregate_frac": ops.get("_all", {}).get("frac")},
+            "roofline_nvlink": nvlink_roofline(v["ar"], world),
+            "parity": parity,
+            "step_ms": {"value": v["step_ms"], "e2e": e["step_ms"]},
+            "slowest_rank": {"value": v["slowest_rank"], "e2e": e["slowest_rank"]},
             "clocks": results.get("clocks"),
             "wall_ms_per_step": round(v["wall_ms"] / K, 4),
             "frames_per_opt_step": {"value": v["frames_per_opt_step"], "e2e": e["frames_per_opt_step"],
@@ -371,8 +494,8 @@ def _run_child(extra_env, argv, timeout):
 
 def cpu_baseline_leg(args):
     """The reference's own CPU path (oracle/_ref) on this box's host cores, bounded sample of the same workload."""
-    out = _run_child({}, ["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "0", "--max-seconds", "75"],
-                     timeout=300)
+    out = _run_child({}, ["--impl", "reference", "--gpus", "1", "--steps", "8", "--warmup", "3", "--max-seconds", "100"],
+                     timeout=400)
     if "cpu_baseline" in out:
         return out["cpu_baseline"]
     return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed",

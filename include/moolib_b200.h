@@ -40,8 +40,12 @@ extern "C" {
 #define MB_ETIMEOUT (-3) /* a peer did not arrive at the allreduce barrier in time */
 #define MB_ESTATE (-4)   /* call made in the wrong state (e.g. peer not imported) */
 #define MB_ENOMEM (-5)
+/* positive status of a gated allreduce round (mb_ar_reduce_gated / mb_ar_result): the summed batch size of all peers
+ * is below the requested minimum, nothing was reduced (replaces: src/accumulator.cc:1051 `size < virtualBatchSize`) */
+#define MB_AR_SHORT 1
 
 typedef void* mb_stream_t; /* cudaStream_t */
+typedef void* mb_event_t;  /* cudaEvent_t */
 
 MB_API int mb_version(void);
 MB_API const char* mb_last_error(void);
@@ -128,13 +132,18 @@ typedef struct mb_ar_handle {
 
 #define MB_AR_MAX_WORLD 8
 #define MB_AR_MAX_SLOTS 4 /* staging slots = moolib's set_parallel_gradients ring (src/accumulator.cc:889-903) */
+/* Every slot owns a ring of 3 staging buffers.  Round k of a slot is reduced out of ring position k mod 3; a rank may
+ * write position (k+1) mod 3 while slow peers are still reading position k, and position (k+2) mod 3 = (k-1) mod 3 is
+ * free because every peer has finished round k-1 before it can take part in round k.  The third buffer is what lets
+ * gradients be PRODUCED in the staging memory (no stage kernel): see mb_ar_buffer. */
+#define MB_AR_BUFS_PER_SLOT 3
 
 /* algorithm selector for mb_ar_allreduce */
 #define MB_AR_ALGO_AUTO 0
 #define MB_AR_ALGO_ONESHOT 1 /* every rank pulls all peers' buffers (P2P loads), lowest latency */
 #define MB_AR_ALGO_TWOSHOT 2 /* reduce-scatter by P2P loads + all-gather by P2P stores, 2(N-1)/N traffic */
 
-/* Allocate rank `rank`'s symmetric staging (nslots x max_bytes, cudaMalloc so it is IPC-exportable), barrier
+/* Allocate rank `rank`'s symmetric staging (nslots x 3 x max_bytes, cudaMalloc so it is IPC-exportable), barrier
  * flags and the pinned result block on `device`.  world <= MB_AR_MAX_WORLD, 1 <= nslots <= MB_AR_MAX_SLOTS.
  * (replaces: src/accumulator.cc:847-874 allocateGradients -- pinned CPU staging) */
 MB_API int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int nslots, mb_ar_ctx** out);
@@ -146,8 +155,19 @@ MB_API int mb_ar_ctx_import(mb_ar_ctx* ctx, int peer_rank, const mb_ar_handle* h
 /* Drop all peer mappings and restart the barrier epoch (group resync: src/group.h:453-461, accumulator.cc:555-575).
  * All ranks must reset together; synchronises the device. */
 MB_API int mb_ar_ctx_reset(mb_ar_ctx* ctx, int new_rank, int new_world);
-/* Device pointer of staging slot `slot` (flat fp32, max_bytes), e.g. so that gradients can be produced in place. */
+/* Device pointer of the CURRENT staging buffer of `slot` (flat fp32, max_bytes): what the next allreduce on the slot
+ * reduces.  == mb_ar_buffer(ctx, slot, 0). */
 MB_API void* mb_ar_staging(mb_ar_ctx* ctx, int slot);
+/* Ring buffer `ahead` positions after the slot's current staging buffer (0 <= ahead < MB_AR_BUFS_PER_SLOT).
+ * ahead = 1 is the buffer that becomes current after the next successful round: a host that points its gradient
+ * tensors at it (flat layout of mb_ar_stage, zero-filled) has its next contribution staged by construction -- backward()
+ * writes where the peers will read, K-A1 never runs.
+ * (replaces: src/accumulator.cc:847-874 allocateGradients + :941-980 the D2H staging copies) */
+MB_API void* mb_ar_buffer(mb_ar_ctx* ctx, int slot, int ahead);
+/* Move the slot's ring to the next buffer.  mb_ar_allreduce does this itself after every launch; after
+ * mb_ar_reduce_gated the HOST calls it once it has seen the round end with status MB_OK (a round that ended MB_AR_SHORT
+ * reduced nothing and keeps accumulating into the same staging buffer).  All ranks advance together. */
+MB_API int mb_ar_slot_advance(mb_ar_ctx* ctx, int slot);
 MB_API int mb_ar_world(mb_ar_ctx* ctx);
 MB_API int mb_ar_rank(mb_ar_ctx* ctx);
 
@@ -170,6 +190,25 @@ MB_API int mb_ar_stage(mb_ar_ctx* ctx, int slot, const float* const* grads, cons
 MB_API int mb_ar_allreduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* const* dst, const uint64_t* numel,
                     int ntensors, float* flat_dst, uint64_t flat_numel, int scale_by_num_gradients, int algo,
                     uint32_t timeout_ms, mb_stream_t stream);
+
+/* K-A0 + K-A2  gated allreduce: the virtual-batch gate of moolib's Accumulator evaluated ON THE DEVICE.
+ *   launch 1 (K-A0, one warp): push my_hdr into every peer's sync block, wait for theirs (bounded by timeout_ms / mb_ar_abort),
+ *            sum them; gate open  <=>  sum(batch_size) >= min_batch_size.
+ *   launch 2 (K-A2): gate open -> reduce exactly as mb_ar_allreduce but without its start barrier (a peer's header only
+ *            arrives after its staging is complete); gate closed -> returns immediately.
+ * Result (mb_ar_result, once the stream has passed both launches): status MB_OK + summed header when reduced,
+ * MB_AR_SHORT + summed header when the gate was closed, MB_ETIMEOUT when a peer did not show up.  Every rank reaches the
+ * same verdict (same headers, same min_batch_size).  The slot's ring does NOT advance: call mb_ar_slot_advance after MB_OK.
+ * With world == 1 the gate is evaluated on the host and only K-A2 is launched (or nothing, when short).
+ * `mid_event` (may be NULL) is recorded on `stream` between the two launches, so that a host that brackets the call with
+ * its own events can tell the wait for the slowest peer (K-A0) from the data movement (K-A2).
+ * Returns the number of kernel launches.
+ * (replaces: src/accumulator.cc:1035-1078 startCount -- an 8-byte allreduce over the RPC tree and one extra update() tick
+ *  per step -- and :1005-1033 startReduce) */
+MB_API int mb_ar_reduce_gated(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, uint64_t min_batch_size,
+                       float* const* dst, const uint64_t* numel, int ntensors, float* flat_dst, uint64_t flat_numel,
+                       int scale_by_num_gradients, int algo, uint32_t timeout_ms, mb_event_t mid_event,
+                       mb_stream_t stream);
 
 /* Result of the most recent allreduce on `slot`: summed header and status (0 ok, MB_ETIMEOUT ...).  Reads pinned
  * host memory written by the kernel; only meaningful once the stream has reached the end of that allreduce

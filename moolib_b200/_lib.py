@@ -13,6 +13,8 @@ MB_AR_ALGO_AUTO, MB_AR_ALGO_ONESHOT, MB_AR_ALGO_TWOSHOT = 0, 1, 2
 MB_AR_HANDLE_BYTES = 192
 MB_AR_MAX_WORLD = 8
 MB_AR_MAX_SLOTS = 4
+MB_AR_BUFS_PER_SLOT = 3
+MB_AR_SHORT = 1
 MB_COPY_MAX_INLINE_JOBS = 64
 
 # every symbol include/moolib_b200.h declares (tests check the .so exports all of them)
@@ -21,7 +23,7 @@ SYMBOLS = [
     "mb_copy2d_batch", "mb_gather_rows", "mb_stack_slot", "mb_cat_narrow", "mb_scatter_actions",
     "mb_ar_ctx_create", "mb_ar_ctx_destroy", "mb_ar_ctx_export", "mb_ar_ctx_import", "mb_ar_ctx_reset",
     "mb_ar_staging", "mb_ar_world", "mb_ar_rank", "mb_ar_stage", "mb_ar_allreduce", "mb_ar_result",
-    "mb_ar_flat_numel", "mb_ar_abort",
+    "mb_ar_flat_numel", "mb_ar_abort", "mb_ar_buffer", "mb_ar_slot_advance", "mb_ar_reduce_gated",
 ]
 
 
@@ -86,6 +88,11 @@ def load():
     L.mb_ar_flat_numel.argtypes = [ctypes.POINTER(u64), ci]
     L.mb_ar_flat_numel.restype = u64
     L.mb_ar_abort.argtypes = [vp]
+    L.mb_ar_buffer.argtypes = [vp, ci, ci]
+    L.mb_ar_buffer.restype = vp
+    L.mb_ar_slot_advance.argtypes = [vp, ci]
+    L.mb_ar_reduce_gated.argtypes = [vp, ci, ctypes.POINTER(ArHdr), u64, ctypes.POINTER(vp), ctypes.POINTER(u64), ci, vp,
+                                     u64, ci, ci, u32, vp, vp]
     _lib = L
     return L
 
@@ -219,6 +226,38 @@ class ArContext:
         h = ArHdr(*hdr)
         return check(self.L.mb_ar_allreduce(self._ctx, slot, ctypes.byref(h), None, None, 0, dst.data_ptr(),
                                             dst.numel(), int(scale), algo, timeout_ms, _stream_ptr(stream)))
+
+    def buffer_ptr(self, slot=0, ahead=0):
+        return self.L.mb_ar_buffer(self._ctx, slot, ahead)
+
+    def buffer(self, numel, slot=0, ahead=0):
+        """The ring buffer `ahead` positions after the slot's current staging buffer, as a flat fp32 torch tensor
+        (no copy: gradients written here are staged by construction)."""
+        import torch
+
+        class _Mem:
+            pass
+
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "version": 3,
+                                      "data": (int(self.buffer_ptr(slot, ahead)), False)}
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(m, device=f"cuda:{self.device}")
+
+    def advance(self, slot=0):
+        check(self.L.mb_ar_slot_advance(self._ctx, slot))
+
+    def reduce_gated(self, min_batch, dst_tensors=None, flat_dst=None, hdr=(1, 0, 1, 1), slot=0, scale=True,
+                     algo=MB_AR_ALGO_AUTO, timeout_ms=30000, stream=None):
+        """K-A0 gate + K-A2 reduce; the caller advances the ring after seeing status MB_OK."""
+        h = ArHdr(*hdr)
+        if dst_tensors is not None:
+            ptrs, numel, n = self._lists(dst_tensors)
+            return check(self.L.mb_ar_reduce_gated(self._ctx, slot, ctypes.byref(h), min_batch, ptrs, numel, n, None, 0,
+                                                   int(scale), algo, timeout_ms, None, _stream_ptr(stream)))
+        return check(self.L.mb_ar_reduce_gated(self._ctx, slot, ctypes.byref(h), min_batch, None, None, 0,
+                                               flat_dst.data_ptr(), flat_dst.numel(), int(scale), algo, timeout_ms,
+                                               None, _stream_ptr(stream)))
 
     def result(self, slot=0):
         h = ArHdr()

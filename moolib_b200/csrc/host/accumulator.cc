@@ -5,11 +5,18 @@
 // asynchronous contract (results are applied only inside update(), src/accumulator.cc:508-551), same virtual-batch gate
 // (count allreduce, :1035-1078), leader election by max (modelVersion, name) (:581-625), late-joiner model/state sync
 // (:464-488, :719-836).  What changes for CUDA parameters:
-//   reduce_gradients(): ONE stage launch (K-A1: staging (=|+=) grads, grads <- 0) instead of 36 D2H copy_ + 36 zero_
-//                       (:941-980, :410-418); no stream synchronize (:937) -- everything stays stream-ordered.
-//   when the count gate opens: ONE allreduce launch (K-A2) that pulls every peer's staging over NVLink, sums in rank
-//                       order, multiplies by 1.0f/numGradients and writes the .grad tensors -- instead of the RPC tree
-//                       (src/group.h:570-654), 36 H2D copy_ and 36 mul_ (:441-442) and a stream synchronize (:450).
+//   gradients LIVE in the NVLink staging memory: every parameter's .grad is a view into the slot's current ring buffer
+//                       (mb_ar_buffer), so backward() writes where the peers read and reduce_gradients() launches NO
+//                       stage kernel (reference: 36 D2H copy_ + 36 zero_, :941-980, :410-418, and a stream synchronize
+//                       :937).  A foreign .grad (assigned by the user) or a second local contribution before the gate
+//                       opens is folded in by ONE K-A1 launch.
+//   the virtual-batch gate is evaluated ON THE DEVICE (K-A0, one warp) right behind the backward pass -- no count
+//                       allreduce over the control plane (:1035-1078) and no extra update() tick -- and is followed
+//                       stream-ordered by ONE K-A2 launch that pulls every peer's staging over NVLink, sums in rank
+//                       order, multiplies by 1.0f/numGradients and writes the slot's result buffer, which .grad is
+//                       pointed at when update() applies the result (reference: RPC tree src/group.h:570-654, 36 H2D
+//                       copy_ + 36 mul_ :441-442, stream synchronize :450).
+// MOOLIB_B200_STRICT_COUNTING=0 restores the reference's accumulate-while-counting with the count on the control plane.
 // CPU parameters (BASELINE.json config 0, "plumbing, no GPU") reduce over the control plane in member order.
 #include "common.h"
 #include "control.h"
@@ -30,13 +37,15 @@ struct ReduceSlot {
   std::shared_ptr<SmallReduce> countOp;
   std::shared_ptr<SmallReduce> reduceOp;   // CPU-parameter path
   std::vector<torch::Tensor> cpuStaging;   // CPU-parameter path (src/accumulator.cc:847-874)
-  cudaEvent_t event = nullptr;             // device path: completion of the K-A2 launch
-  cudaEvent_t staged = nullptr;            // device path: the last K-A1 of this slot has run (compute stream)
+  cudaEvent_t event = nullptr;             // device path: completion of the K-A2 launch (timing enabled)
+  cudaEvent_t staged = nullptr;            // device path: this slot's gradients are complete (compute stream)
+  cudaEvent_t evBegin = nullptr, evMid = nullptr;  // device gate: before K-A0 / between K-A0 and K-A2 (timing)
   bool kernelInFlight = false;
+  bool gated = false;                      // the in-flight launch is K-A0 + K-A2 (mb_ar_reduce_gated)
   Clock::time_point reduceStart;
   ~ReduceSlot() {
-    if (event) cudaEventDestroy(event);
-    if (staged) cudaEventDestroy(staged);
+    for (cudaEvent_t e : {event, staged, evBegin, evMid})
+      if (e) cudaEventDestroy(e);
   }
 };
 
@@ -146,6 +155,10 @@ class Accumulator {
   }
 
   ~Accumulator() {
+    try {
+      releaseGradViews();
+    } catch (...) {
+    }
     if (arStream_) cudaStreamDestroy(arStream_);
     unhandleAll(*parts_.rpc, {"Acc::requestModel/" + resName_, "Acc::modelUpdate/" + resName_,
                               "Acc::buffersUpdate/" + resName_});
@@ -186,10 +199,19 @@ class Accumulator {
     if (strictCounting_ && v->isCounting) return false;
     return true;
   }
+  bool anyKernelInFlight() {
+    for (auto& v : slots_)
+      if (v && v->kernelInFlight) return true;
+    return false;
+  }
   bool wantsGradientsLocked() {
+    // Host-counted CUDA path (MOOLIB_B200_STRICT_COUNTING=0): its K-A2 writes the .grad tensors themselves, so no new
+    // backward may start while any slot's kernel is in flight (set_parallel_gradients(n>1) would otherwise race with it).
+    if (gradsOnCuda_ && !deviceGate() && anyKernelInFlight()) return false;
     return connectedImpl() && wantsGradientsAtIndex(nextIndex_) && !isWaitingForModel_ && !isFindingLeader_ &&
            !hasGradients_ && (!gradsOnCuda_ || reducerReady_);
   }
+  bool deviceGate() const { return gradsOnCuda_ && strictCounting_; }
   bool wantsGradients() {
     std::lock_guard<std::mutex> l(mu_);
     return wantsGradientsLocked();
@@ -232,7 +254,126 @@ class Accumulator {
   void zeroGradients() {
     std::lock_guard<std::mutex> l(mu_);
     hasGradients_ = false;
+    if (deviceGate() && reducerReady_ && arena_) {
+      torch::NoGradGuard ng;
+      c10::cuda::CUDAGuard dg(device_);
+      GradViews& av = viewsOf(accumBase(nextIndex_));
+      if (gradsAre(av) || (appliedSlot_ >= 0 && gradsAre(viewsOf(arena_->result[appliedSlot_].data_ptr<float>())))) {
+        // .grad shows an applied result (or is already accumulating): (back) to the accumulation buffer, zero-filled by
+        // ONE memset of the flat buffer (reference: 36 zero_ launches, src/accumulator.cc:410-418)
+        cudaMemsetAsync(av.base, 0, (size_t)arena_->total * 4, c10::cuda::getCurrentCUDAStream(device_).stream());
+        pointGradsAt(av);
+      } else {
+        actuallyZeroGradients();
+      }
+      appliedSlot_ = -1;
+      return;
+    }
     actuallyZeroGradients();
+  }
+
+  // ---- gradient arena (device gate path): .grad tensors are views into the symmetric ring / the result buffers ----
+  struct GradViews {
+    float* base = nullptr;
+    torch::Tensor flat;
+    std::vector<torch::Tensor> v;  // one per parameter that requires grad, same order as ensureGrads()
+  };
+  struct GradArena {
+    std::vector<int64_t> numel, off;  // floats; off = flat layout of mb_ar_stage (each tensor starts 16 B aligned)
+    std::vector<std::vector<int64_t>> sizes;
+    int64_t total = 0;                // padded floats
+    std::map<float*, GradViews> views;
+    std::vector<torch::Tensor> result;  // per slot: where K-A2 writes (local memory, flat layout)
+  };
+
+  GradArena& arena() {
+    if (!arena_) {
+      arena_ = std::make_unique<GradArena>();
+      int64_t off = 0;
+      for (auto& p : params_) {
+        if (!p.requires_grad()) continue;
+        arena_->numel.push_back(p.numel());
+        arena_->off.push_back(off);
+        arena_->sizes.emplace_back(p.sizes().begin(), p.sizes().end());
+        off += (p.numel() + 3) & ~int64_t(3);
+      }
+      arena_->total = off;
+      c10::cuda::CUDAGuard dg(device_);
+      for (size_t i = 0; i < slots_.size(); ++i)
+        arena_->result.push_back(torch::empty({std::max<int64_t>(off, 4)}, torch::dtype(torch::kFloat32).device(torch::kCUDA, device_)));
+    }
+    return *arena_;
+  }
+
+  GradViews& viewsOf(float* base) {
+    GradArena& a = arena();
+    auto it = a.views.find(base);
+    if (it != a.views.end()) return it->second;
+    GradViews& gv = a.views[base];
+    gv.base = base;
+    gv.flat = torch::from_blob(base, {std::max<int64_t>(a.total, 1)}, torch::dtype(torch::kFloat32).device(torch::kCUDA, device_));
+    for (size_t i = 0; i < a.numel.size(); ++i) gv.v.push_back(gv.flat.narrow(0, a.off[i], a.numel[i]).view(a.sizes[i]));
+    return gv;
+  }
+
+  bool gradsAre(const GradViews& gv) {
+    size_t i = 0;
+    for (auto& p : params_) {
+      if (!p.requires_grad()) continue;
+      const torch::Tensor& g = p.grad();
+      if (!g.defined() || g.data_ptr() != gv.v[i].data_ptr() || g.scalar_type() != torch::kFloat32 || !g.is_contiguous())
+        return false;
+      ++i;
+    }
+    return true;
+  }
+
+  void pointGradsAt(GradViews& gv) {
+    size_t i = 0;
+    for (auto& p : params_) {
+      if (!p.requires_grad()) continue;
+      p.mutable_grad() = gv.v[i++];
+    }
+  }
+
+  bool slotHoldsData(size_t j) {
+    auto& v = slots_[j];
+    return v && !v->reduceDone && v->data.has_grads != 0;
+  }
+  // Where the next contribution for slot j is accumulated: the slot's staging itself while it is empty (zero-copy: the
+  // peers will read exactly what backward() wrote), else the next ring buffer (folded in by K-A1).
+  float* accumBase(size_t j) {
+    return static_cast<float*>(mb_ar_buffer(reducer()->ctx(), (int)j, slotHoldsData(j) ? 1 : 0));
+  }
+
+  // Point .grad at the accumulation buffer of the slot that the next reduce_gradients() call fills.
+  void repointForAccumulation() {
+    c10::cuda::CUDAGuard dg(device_);
+    GradViews& av = viewsOf(accumBase(nextIndex_));
+    if (gradsAre(av)) return;  // already there (and clean: K-A1 zeroes its sources)
+    cudaMemsetAsync(av.base, 0, (size_t)arena().total * 4, c10::cuda::getCurrentCUDAStream(device_).stream());
+    pointGradsAt(av);
+  }
+
+  bool gradsInArena() {
+    if (!arena_) return false;
+    for (auto& kv : arena_->views)
+      if (gradsAre(kv.second)) return true;
+    return false;
+  }
+
+  // Give every parameter an ordinary .grad tensor again (same values): before the arena's memory goes away.
+  void releaseGradViews() {
+    if (!arena_) return;
+    torch::NoGradGuard ng;
+    if (gradsInArena()) {
+      for (auto& p : params_) {
+        if (!p.requires_grad() || !p.grad().defined()) continue;
+        p.mutable_grad() = p.grad().clone();
+      }
+    }
+    arena_.reset();
+    appliedSlot_ = -1;
   }
 
   uint64_t flatBytes(const std::vector<torch::Tensor>& gs) {
@@ -261,7 +402,14 @@ class Accumulator {
     if (target && target->reduceStarted && !target->reduceDone)
       throw std::runtime_error("reduceImpl internal error, reduce already started!");
     if (!target || target->reduceDone) {
-      target = slots_[index] = std::make_shared<ReduceSlot>();
+      auto fresh = std::make_shared<ReduceSlot>();
+      if (target) {  // keep the CUDA events (creating four per round costs more than the gate kernel)
+        std::swap(fresh->event, target->event);
+        std::swap(fresh->staged, target->staged);
+        std::swap(fresh->evBegin, target->evBegin);
+        std::swap(fresh->evMid, target->evMid);
+      }
+      target = slots_[index] = fresh;
       target->index = index;
     }
     nextIndex_ = (nextIndex_ == slots_.size() - 1) ? 0 : nextIndex_ + 1;
@@ -273,19 +421,25 @@ class Accumulator {
       auto gs = ensureGrads();
       const bool add = target->data.has_grads != 0;
       if (gradsOnCuda_) {
-        // K-A1: staging (=|+=) grads and grads <- 0 in one launch, ordered after backward() on the current stream
-        std::vector<const float*> ptrs;
-        std::vector<uint64_t> numel;
-        for (auto& g : gs) {
-          ptrs.push_back(g.data_ptr<float>());
-          numel.push_back((uint64_t)g.numel());
-        }
         c10::cuda::CUDAGuard dg(device_);
-        launch_counter() += check(mb_ar_stage(reducer()->ctx(), (int)index, ptrs.data(), numel.data(), (int)gs.size(),
-                                              add ? 1 : 0, /*zero_src=*/1, current_stream(device_)),
-                                  "Accumulator.reduce_gradients");
-        if (!target->staged) cudaEventCreateWithFlags(&target->staged, cudaEventDisableTiming);
-        cudaEventRecord(target->staged, c10::cuda::getCurrentCUDAStream(device_).stream());
+        const bool zeroCopy = deviceGate() && !add &&
+                              gradsAre(viewsOf(static_cast<float*>(mb_ar_buffer(reducer()->ctx(), (int)index, 0))));
+        if (!zeroCopy) {
+          // K-A1: staging (=|+=) grads and grads <- 0 in one launch, ordered after backward() on the current stream
+          // (a user-assigned .grad, or another local contribution while the gate is still closed)
+          std::vector<const float*> ptrs;
+          std::vector<uint64_t> numel;
+          for (auto& g : gs) {
+            ptrs.push_back(g.data_ptr<float>());
+            numel.push_back((uint64_t)g.numel());
+          }
+          launch_counter() += check(mb_ar_stage(reducer()->ctx(), (int)index, ptrs.data(), numel.data(), (int)gs.size(),
+                                                add ? 1 : 0, /*zero_src=*/1, current_stream(device_)),
+                                    "Accumulator.reduce_gradients");
+          ++stageLaunches_;
+        } else {
+          ++zeroCopyRounds_;
+        }
       } else {
         if (!add) {
           target->cpuStaging.clear();
@@ -299,8 +453,15 @@ class Accumulator {
     } else {
       ++target->data.num_skipped;
     }
+    if (gradsOnCuda_) {
+      c10::cuda::CUDAGuard dg(device_);
+      if (deviceGate()) repointForAccumulation();
+      if (!target->staged) cudaEventCreateWithFlags(&target->staged, cudaEventDisableTiming);
+      cudaEventRecord(target->staged, c10::cuda::getCurrentCUDAStream(device_).stream());
+    }
     if (target->syncId == hSyncId_ && target->syncId == parts_.info->syncId.load()) {
-      if (target->isCounting) target->wantsMoreCounting = true;
+      if (deviceGate()) startGatedReduce(target);
+      else if (target->isCounting) target->wantsMoreCounting = true;
       else startCount(target);
     }
     MBH_PHASE("idle");
@@ -308,7 +469,43 @@ class Accumulator {
   void reduceGradients(int batchSize) { reduceImpl(batchSize); }
   void skipGradients() { reduceImpl(0); }
 
-  // reference: startCount, src/accumulator.cc:1035-1078
+  cudaStream_t reduceStream() {
+    // K-A0/K-A2 run on their own high-priority stream, ordered only after the slot's gradients are complete: they must
+    // not queue behind actor-inference work the loop has enqueued on the compute stream since then (tens of ms at 256
+    // envs), because every peer's round waits for the slowest rank to reach its gate.
+    if (!arStream_) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&arStream_, cudaStreamNonBlocking, hi) != cudaSuccess) arStream_ = nullptr;
+    }
+    return arStream_ ? arStream_ : c10::cuda::getCurrentCUDAStream(device_).stream();
+  }
+
+  // Device gate (replaces startCount + startReduce, src/accumulator.cc:1005-1078): K-A0 sums every peer's
+  // {numGradients, numSkipped, batchSize} over NVLink and opens the gate when sum(batchSize) >= virtualBatchSize; K-A2
+  // follows on the same stream and reduces into the slot's result buffer, or returns at once when the gate stayed shut.
+  void startGatedReduce(const std::shared_ptr<ReduceSlot>& target) {
+    MBH_PHASE("startGatedReduce");
+    c10::cuda::CUDAGuard dg(device_);
+    GradArena& a = arena();
+    cudaStream_t stream = reduceStream();
+    if (target->staged) cudaStreamWaitEvent(stream, target->staged, 0);
+    for (cudaEvent_t* e : {&target->evBegin, &target->evMid, &target->event})
+      if (!*e) cudaEventCreate(e);
+    cudaEventRecord(target->evBegin, stream);
+    target->isCounting = true;
+    target->gated = true;
+    target->reduceStart = Clock::now();
+    launch_counter() += check(
+        mb_ar_reduce_gated(reducer()->ctx(), (int)target->index, &target->data, virtualBatchSize_, nullptr, nullptr, 0,
+                           a.result[target->index].data_ptr<float>(), (uint64_t)a.total, /*scale=*/1, MB_AR_ALGO_AUTO,
+                           (uint32_t)(parts_.rpc->getTimeout() * 1000), target->evMid, static_cast<mb_stream_t>(stream)),
+        "Accumulator gated allreduce");
+    cudaEventRecord(target->event, stream);
+    target->kernelInFlight = true;
+  }
+
+  // reference: startCount, src/accumulator.cc:1035-1078 (host-counted path: CPU parameters, MOOLIB_B200_STRICT_COUNTING=0)
   void startCount(const std::shared_ptr<ReduceSlot>& target) {
     MBH_PHASE("startCount");
     if (target->syncId != hSyncId_ || target->syncId != parts_.info->syncId.load()) return;
@@ -342,28 +539,22 @@ class Accumulator {
         numel.push_back((uint64_t)g.numel());
       }
       c10::cuda::CUDAGuard dg(device_);
-      // K-A2 runs on its own high-priority stream, ordered only after this slot's last stage kernel: it must not queue
-      // behind actor-inference work the loop has enqueued on the compute stream since then (tens of ms at 256 envs),
-      // because every peer's round waits for the slowest rank to reach its allreduce kernel.  Safe: all backward passes
-      // that contributed were followed by their stage kernel in the same reduce_gradients() call, no new backward can
-      // be enqueued once the reduce has started (wants_gradients() is false), and the compute stream is made to wait
-      // for the kernel before has_gradients() turns true.
-      if (!arStream_) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&arStream_, cudaStreamNonBlocking, hi) != cudaSuccess) arStream_ = nullptr;
-      }
-      cudaStream_t stream = arStream_ ? arStream_ : c10::cuda::getCurrentCUDAStream(device_).stream();
-      if (arStream_ && target->staged) cudaStreamWaitEvent(arStream_, target->staged, 0);
+      // Host-counted path: K-A2 (with its in-kernel barrier) writes the .grad tensors themselves.  Safe: every backward
+      // pass that contributed was followed by its stage kernel in the same reduce_gradients() call, no new backward is
+      // allowed while a kernel is in flight (wantsGradientsLocked), and the compute stream waits for the kernel before
+      // has_gradients() turns true.
+      cudaStream_t stream = reduceStream();
+      if (target->staged) cudaStreamWaitEvent(stream, target->staged, 0);
       // K-A2: barrier + P2P reduce + 1/numGradients scale + scatter into the .grad tensors, one launch
       launch_counter() += check(
           mb_ar_allreduce(reducer()->ctx(), (int)target->index, &target->data, ptrs.data(), numel.data(), (int)gs.size(),
                           nullptr, 0, /*scale=*/1, MB_AR_ALGO_AUTO, (uint32_t)(parts_.rpc->getTimeout() * 1000),
                           static_cast<mb_stream_t>(stream)),
           "Accumulator allreduce");
-      if (!target->event) cudaEventCreateWithFlags(&target->event, cudaEventDisableTiming);
+      if (!target->event) cudaEventCreate(&target->event);
       cudaEventRecord(target->event, stream);
       target->kernelInFlight = true;
+      target->gated = false;
     } else {
       try {
         target->reduceOp = parts_.service->allReduce(
@@ -418,14 +609,29 @@ class Accumulator {
         mb_ar_hdr total;
         int status = 0;
         mb_ar_result(reducer()->ctx(), (int)v->index, &total, &status);
-        if (e != cudaSuccess || status != 0) {
+        if (e != cudaSuccess || status < 0) {
           lastError_ = e != cudaSuccess ? std::string(cudaGetErrorString(e))
                                         : (status == MB_ETIMEOUT ? "allreduce barrier timed out" : "allreduce failed");
           v->reduceDone = true;  // abandon the round; the resync resets the slots
           onError();
+        } else if (v->gated && status == MB_AR_SHORT) {
+          // gate closed (src/accumulator.cc:1051): keep accumulating; the next reduce/skip call counts again
+          ran = false;
+          v->isCounting = false;
+          ++shortRounds_;
+          recordTiming(*v, /*reduced=*/false);
         } else {
           // later work on the compute stream (clip_grad_norm_, optimizer.step) is ordered after the kernel
+          c10::cuda::CUDAGuard dg(device_);
           cudaStreamWaitEvent(c10::cuda::getCurrentCUDAStream(device_).stream(), v->event, 0);
+          if (v->gated) {
+            v->reduceStarted = true;
+            recordTiming(*v, /*reduced=*/true);
+            check(mb_ar_slot_advance(reducer()->ctx(), (int)v->index), "mb_ar_slot_advance");
+            torch::NoGradGuard ng;
+            pointGradsAt(viewsOf(arena().result[v->index].data_ptr<float>()));
+            appliedSlot_ = (int)v->index;
+          }
           finishReduce(v, total);
         }
       }
@@ -670,6 +876,12 @@ class Accumulator {
       auto r = reducer();
       if (r->failed()) throw std::runtime_error(r->error());
       reducerReady_ = r->poll() && r->syncId() == hSyncId_;
+      if (reducerReady_ && deviceGate() && gradsInArena()) {
+        // new group epoch: the ring restarted at position 0; move .grad off whatever buffer it pointed at
+        torch::NoGradGuard ng2;
+        appliedSlot_ = -1;
+        repointForAccumulation();
+      }
     }
     MBH_PHASE("update:checkGradientResult");
     checkGradientResult();
@@ -797,11 +1009,49 @@ class Accumulator {
     if (n < 1 || n > MB_AR_MAX_SLOTS)
       throw std::runtime_error("set_parallel_gradients: n must be in [1, " + std::to_string(MB_AR_MAX_SLOTS) + "]");
     std::lock_guard<std::mutex> l(mu_);
+    releaseGradViews();
     slots_.clear();
     slots_.resize(n);
     nextIndex_ = nextResultIndex_ = 0;
     reducer_.reset();
     reducerReady_ = false;
+  }
+
+  // ---- device-side round timings (bench.py: roofline_nvlink) -------------------------------------------------------
+  void recordTiming(ReduceSlot& v, bool reduced) {
+    float gateMs = 0.f, reduceMs = 0.f;
+    if (!v.evBegin || !v.evMid || !v.event) return;
+    if (cudaEventElapsedTime(&gateMs, v.evBegin, v.evMid) != cudaSuccess ||
+        cudaEventElapsedTime(&reduceMs, v.evMid, v.event) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    if (timings_.size() >= 65536) return;
+    timings_.push_back({gateMs * 1e3f, reduceMs * 1e3f, reduced});
+  }
+  py::dict reduceTimings(bool clear) {
+    std::lock_guard<std::mutex> l(mu_);
+    py::list gate, red, ok;
+    for (auto& t : timings_) {
+      gate.append(t.gateUs);
+      red.append(t.reduceUs);
+      ok.append(t.reduced);
+    }
+    py::dict d;
+    d["gate_us"] = gate;      // K-A0: includes the wait for the slowest peer
+    d["reduce_us"] = red;     // K-A2: the data movement
+    d["reduced"] = ok;        // false: the gate stayed shut (short batch), K-A2 returned at once
+    d["bytes"] = arena_ ? (int64_t)arena_->total * 4 : (int64_t)0;
+    d["world"] = reducer_ ? reducer_->world() : 0;
+    d["stage_launches"] = stageLaunches_;
+    d["zero_copy_rounds"] = zeroCopyRounds_;
+    d["short_rounds"] = shortRounds_;
+    d["device_gate"] = deviceGate();
+    if (clear) {
+      timings_.clear();
+      stageLaunches_ = zeroCopyRounds_ = shortRounds_ = 0;
+    }
+    return d;
   }
   std::string getLeader() {
     std::lock_guard<std::mutex> l(mu_);
@@ -824,6 +1074,14 @@ class Accumulator {
   std::shared_ptr<DeviceReducer> reducer_;
   bool reducerReady_ = false;
   cudaStream_t arStream_ = nullptr;
+  std::unique_ptr<GradArena> arena_;
+  int appliedSlot_ = -1;  // slot whose result buffer .grad currently shows (-1: none)
+  struct RoundTiming {
+    float gateUs, reduceUs;
+    bool reduced;
+  };
+  std::vector<RoundTiming> timings_;
+  uint64_t stageLaunches_ = 0, zeroCopyRounds_ = 0, shortRounds_ = 0;
   bool strictCounting_ = [] {
     const char* e = std::getenv("MOOLIB_B200_STRICT_COUNTING");
     return !(e && *e == '0');
@@ -881,7 +1139,9 @@ void bind_accumulator(py::module_& m) {
       .def("get_leader", &Accumulator::getLeader)
       .def("is_leader", &Accumulator::isLeader)
       .def("get_gradient_stats", &Accumulator::getGradientStats)
-      .def("debug_state", &Accumulator::debugState);
+      .def("debug_state", &Accumulator::debugState)
+      .def("reduce_timings", &Accumulator::reduceTimings, py::arg("clear") = false,
+           "CUDA-event timings of every device-gated round: K-A0 (gate, waits for the slowest peer) and K-A2 (reduce)");
 }
 
 }  // namespace mbh

@@ -9,6 +9,12 @@
 //         ar_twoshot_kernel  : reduce-scatter by P2P loads (rank r reduces slice r), all-gather by P2P stores into
 //                              every peer's staging, second flag barrier, local scatter.  2(N-1)/N*S per direction.
 // Both give bit-identical results on every rank and identical to each other (same summation order).
+//   K-A0  ar_gate_kernel     : ONE 32-thread CTA.  Pushes this rank's {numGradients,numSkipped,batchSize,has_grads}
+//                              into every peer's sync block, waits for theirs, sums them and decides whether the
+//                              virtual-batch gate is open (sum(batchSize) >= min_batch).  The reduce kernel that
+//                              follows on the stream reads the decision: closed -> it returns at once, open -> it needs
+//                              no start barrier (every peer's staging is complete once its header has arrived).
+//                              Replaces the count allreduce over RPC (src/accumulator.cc:1035-1078).
 //
 // Reference semantics being replaced: src/accumulator.cc:941-980 (stage), src/group.h:195-212 (add),
 // src/group.h:570-654,687-787 (tree reduce + share), src/accumulator.cc:425-452 (copy_ + mul_(1.0f/numGradients)).
@@ -42,6 +48,18 @@ struct SyncBlock {
   mb_ar_hdr hdr[2];                                 // [epoch parity], written by the owner before it signals
   uint32_t flagsA[kArMaxBlocks][MB_AR_MAX_WORLD];   // [block][source rank] = epoch: "my data for this round is staged"
   uint32_t flagsB[kArMaxBlocks][MB_AR_MAX_WORLD];   // two-shot: "my reduced slice is written to your staging"
+  // gated rounds (K-A0): headers are PUSHED by their owner into every peer's block, then the flag is released
+  mb_ar_hdr ghdr[2][MB_AR_MAX_WORLD];               // [epoch parity][source rank]
+  uint32_t gate[MB_AR_MAX_WORLD];                   // [source rank] = epoch: "my header is in, my staging is complete"
+};
+
+// Written by the gate kernel, read by the reduce kernel that follows it on the stream (device-local).
+struct GateOut {
+  mb_ar_hdr tot;
+  uint32_t mask;      // ranks with has_grads
+  int32_t decision;   // 1 = reduce, 0 = gate closed (short batch) or barrier failure: the reduce kernel returns
+  uint32_t epoch;
+  uint32_t pad;
 };
 
 struct HostResult {
@@ -90,7 +108,7 @@ struct mb_ar_ctx {
   uint64_t max_bytes = 0;  // per staging buffer, multiple of 16
   void* block = nullptr;             // the one IPC-exported allocation: [staging | SyncBlock], multiple of 2 MiB
   uint64_t block_bytes = 0, sync_offset = 0;
-  float* staging = nullptr;          // nslots * 2 buffers (parity double-buffering, see mb_ar_allreduce)
+  float* staging = nullptr;          // nslots * MB_AR_BUFS_PER_SLOT buffers (ring, see mb_ar_allreduce)
   mb::SyncBlock* sync = nullptr;
   void* peer_block[MB_AR_MAX_WORLD] = {};  // IPC-opened base of each peer's block (what must be closed)
   float* peer_staging[MB_AR_MAX_WORLD] = {};
@@ -103,6 +121,7 @@ struct mb_ar_ctx {
   mb::HostResult* result_dev = nullptr;
   uint32_t* abort_host = nullptr;
   uint32_t* abort_dev = nullptr;
+  mb::GateOut* gate_out = nullptr;   // device, one per slot
   mb::TensorEnt* tab_dev[2] = {nullptr, nullptr};  // 0: stage sources, 1: allreduce destinations
   std::vector<mb::TensorEnt> tab_host[2];
   std::mutex mu;
@@ -112,9 +131,11 @@ namespace mb {
 namespace {
 
 struct ArParams {
-  float* stage[MB_AR_MAX_WORLD];     // every rank's staging buffer for this slot/parity ([rank] = own)
+  float* stage[MB_AR_MAX_WORLD];     // every rank's staging buffer for this slot/ring position ([rank] = own)
   SyncBlock* sync[MB_AR_MAX_WORLD];  // every rank's sync block
-  const TensorEnt* dst_tab;
+  const TensorEnt* dst_tab;          // ntensors entries; ignored when ntensors == 0 (flat destination)
+  float* flat_dst;                   // ntensors == 0: result goes to flat_dst[v*4..], same layout as the staging
+  const GateOut* gate;               // non-null: gated round (K-A0 ran before this kernel on the stream)
   uint32_t ntensors;
   uint32_t epoch;
   uint64_t total_vec;  // flat length in float4 units
@@ -138,30 +159,64 @@ struct StageParams {
   uint64_t total_vec;
 };
 
+struct GateParams {
+  SyncBlock* sync[MB_AR_MAX_WORLD];
+  GateOut* out;
+  HostResult* result;
+  const uint32_t* abort_flag;
+  mb_ar_hdr my_hdr;
+  uint64_t min_batch;
+  uint64_t timeout_ns;
+  uint32_t epoch;
+  int32_t rank;
+  int32_t world;
+};
+
 // ---- flat layout <-> tensor list ---------------------------------------------------------------------------------
 
-// s_off[i] = first float4 of tensor i in the flat layout.  Returns the tensor that owns float4 index v.
-__device__ __forceinline__ uint32_t find_tensor(const uint32_t* s_off, uint32_t n, uint32_t v) {
-  uint32_t lo = 0, hi = n;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (s_off[mid] <= v) lo = mid; else hi = mid;
+// The tensor table lives in dynamic shared memory as three arrays (pointers, numel, first float4).  A thread's flat
+// index only ever grows inside a kernel, so the owning tensor is found by walking a per-thread cursor forward: no
+// per-vector search and no dependent global load (round 1 did a 6-step binary search + a 24 B global load per 16 B of
+// payload -- 0.15 of HBM).
+struct TensorTable {
+  const uint64_t* ptr;
+  const uint64_t* numel;
+  const uint32_t* off;  // first float4 of tensor i
+  uint32_t n;
+};
+
+__device__ __forceinline__ TensorTable load_table(uint8_t* smem, const TensorEnt* tab, uint32_t n) {
+  uint64_t* s_ptr = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* s_numel = s_ptr + n;
+  uint32_t* s_off = reinterpret_cast<uint32_t*>(s_numel + n);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const TensorEnt e = tab[i];
+    s_ptr[i] = e.ptr;
+    s_numel[i] = e.numel;
+    s_off[i] = (uint32_t)(e.off >> 2);
   }
-  return lo;
+  TensorTable t;
+  t.ptr = s_ptr;
+  t.numel = s_numel;
+  t.off = s_off;
+  t.n = n;
+  return t;
 }
 
-__device__ __forceinline__ void load_offsets(uint32_t* s_off, const TensorEnt* tab, uint32_t n) {
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_off[i] = (uint32_t)(tab[i].off >> 2);
+// Advance `cur` to the tensor that owns float4 index v (v never decreases between calls with the same cursor).
+__device__ __forceinline__ void seek_tensor(const TensorTable& tb, uint32_t v, uint32_t& cur) {
+  if (cur + 1 < tb.n && tb.off[cur + 1] <= v) {
+    // jump: binary search over (cur, n) -- taken once per tensor boundary, not once per vector
+    uint32_t lo = cur + 1, hi = tb.n;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (tb.off[mid] <= v) lo = mid; else hi = mid;
+    }
+    cur = lo;
+  }
 }
 
-__device__ __forceinline__ void scatter_vec(const TensorEnt* tab, const uint32_t* s_off, uint32_t n, uint64_t v,
-                                            const float4& r) {
-  const uint32_t t = find_tensor(s_off, n, (uint32_t)v);
-  const TensorEnt e = tab[t];
-  const uint64_t within = v * 4 - e.off;
-  if (within >= e.numel) return;  // padding-only vector (cannot happen for non-empty tensors, kept for safety)
-  float* d = reinterpret_cast<float*>(e.ptr) + within;
-  const uint64_t valid = e.numel - within;
+__device__ __forceinline__ void store_vec(float* d, uint64_t valid, const float4& r) {
   if (valid >= 4 && (reinterpret_cast<uintptr_t>(d) & 15u) == 0) {
     st_f4(d, r);
   } else {
@@ -172,21 +227,33 @@ __device__ __forceinline__ void scatter_vec(const TensorEnt* tab, const uint32_t
   }
 }
 
+__device__ __forceinline__ void scatter_vec(const TensorTable& tb, uint64_t v, const float4& r, uint32_t& cur) {
+  seek_tensor(tb, (uint32_t)v, cur);
+  const uint64_t within = (v - tb.off[cur]) * 4;
+  const uint64_t numel = tb.numel[cur];
+  if (within >= numel) return;  // padding-only vector (empty tensor)
+  store_vec(reinterpret_cast<float*>(tb.ptr[cur]) + within, numel - within, r);
+}
+
 // ---- K-A1 --------------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(kArThreads) ar_stage_kernel(const __grid_constant__ StageParams p) {
-  __shared__ uint32_t s_off[kArMaxTensors];
-  load_offsets(s_off, p.tab, p.ntensors);
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  const TensorTable tb = load_table(dyn_smem, p.tab, p.ntensors);
   __syncthreads();
-  const uint64_t stride = (uint64_t)gridDim.x * kArThreads;
-  for (uint64_t v = (uint64_t)blockIdx.x * kArThreads + threadIdx.x; v < p.total_vec; v += stride) {
-    const uint32_t t = find_tensor(s_off, p.ntensors, (uint32_t)v);
-    const TensorEnt e = p.tab[t];
-    const uint64_t within = v * 4 - e.off;
+  // each block owns a contiguous span of the flat layout: consecutive iterations touch consecutive 8 KiB chunks
+  const uint64_t per_block = (p.total_vec + gridDim.x - 1) / gridDim.x;
+  const uint64_t begin = (uint64_t)blockIdx.x * per_block;
+  const uint64_t end = min(begin + per_block, p.total_vec);
+  uint32_t cur = 0;
+  for (uint64_t v = begin + threadIdx.x; v < end; v += kArThreads) {
+    seek_tensor(tb, (uint32_t)v, cur);
+    const uint64_t within = (v - tb.off[cur]) * 4;
+    const uint64_t numel = tb.numel[cur];
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (within < e.numel) {
-      float* s = reinterpret_cast<float*>(e.ptr) + within;
-      const uint64_t valid = e.numel - within;
+    if (within < numel) {
+      float* s = reinterpret_cast<float*>(tb.ptr[cur]) + within;
+      const uint64_t valid = numel - within;
       const bool vec = valid >= 4 && (reinterpret_cast<uintptr_t>(s) & 15u) == 0;
       if (vec) {
         g = *reinterpret_cast<const float4*>(s);
@@ -196,28 +263,38 @@ __global__ void __launch_bounds__(kArThreads) ar_stage_kernel(const __grid_const
         if (valid > 2) g.z = s[2];
         if (valid > 3) g.w = s[3];
       }
-      if (p.zero_src) {
-        if (vec) {
-          *reinterpret_cast<float4*>(s) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          s[0] = 0.f;
-          if (valid > 1) s[1] = 0.f;
-          if (valid > 2) s[2] = 0.f;
-          if (valid > 3) s[3] = 0.f;
-        }
-      }
+      if (p.zero_src) store_vec(s, valid, make_float4(0.f, 0.f, 0.f, 0.f));
     }
     float4* d = reinterpret_cast<float4*>(p.staging) + v;
     if (p.accumulate) {
       // staged += new  (src/accumulator.cc:975 targetGradients[i].add_(addGrads[i]))
       const float4 a = *d;
-      g = make_float4(a.x + g.x, a.y + g.y, a.z + g.z, a.w + g.w);
+      g = make_float4(__fadd_rn(a.x, g.x), __fadd_rn(a.y, g.y), __fadd_rn(a.z, g.z), __fadd_rn(a.w, g.w));
     }
     *d = g;
   }
 }
 
 // ---- barrier ----------------------------------------------------------------------------------------------------
+
+// Bounded wait until *local >= epoch (relaxed system-scope polling; the caller fences).  Returns false on timeout/abort.
+__device__ __forceinline__ bool wait_flag(const uint32_t* local, uint32_t epoch, uint64_t timeout_ns,
+                                          const uint32_t* abort_flag) {
+  // Poll with RELAXED system-scope loads and fence once after the flag is seen (relaxed load + acquire fence is an
+  // acquire pattern).  An acquire load per poll is a system-scope fence per poll: hundreds of spinning threads doing
+  // that slowed the peers' NVLink reads of this GPU's memory (bimodal 40 us / 150 us rounds at N=4).
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while ((int32_t)(ld_relaxed_sys_u32(local) - epoch) < 0) {
+    __nanosleep(32);
+    if ((++spins & 255u) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > timeout_ns || ld_volatile_u32(abort_flag) != 0) return false;
+    }
+  }
+  return true;
+}
 
 // Every block pairs with the same-numbered block on every peer.  Returns false on timeout / abort.
 __device__ __forceinline__ bool block_barrier(const ArParams& p, bool second) {
@@ -230,22 +307,7 @@ __device__ __forceinline__ bool block_barrier(const ArParams& p, bool second) {
     st_release_sys_u32(remote, p.epoch);
     SyncBlock* me = p.sync[p.rank];
     const uint32_t* local = second ? &me->flagsB[blockIdx.x][t] : &me->flagsA[blockIdx.x][t];
-    // Poll with RELAXED system-scope loads and fence once after the flag is seen (relaxed load + acquire fence is an
-    // acquire pattern).  An acquire load per poll is a system-scope fence per poll: hundreds of spinning threads doing
-    // that slowed the peers' NVLink reads of this GPU's memory (bimodal 40 us / 150 us rounds at N=4).
-    uint32_t spins = 0;
-    uint64_t t0 = 0;
-    while ((int32_t)(ld_relaxed_sys_u32(local) - p.epoch) < 0) {
-      __nanosleep(32);
-      if ((++spins & 255u) == 0) {
-        const uint64_t now = globaltimer_ns();
-        if (t0 == 0) t0 = now;
-        if (now - t0 > p.timeout_ns || ld_volatile_u32(p.abort_flag) != 0) {
-          fail = 1;
-          break;
-        }
-      }
-    }
+    if (!wait_flag(local, p.epoch, p.timeout_ns, p.abort_flag)) fail = 1;
     fence_acq_rel_sys();
   }
   return __syncthreads_or(fail) == 0;
@@ -254,6 +316,67 @@ __device__ __forceinline__ bool block_barrier(const ArParams& p, bool second) {
 __device__ __forceinline__ void report_failure(const ArParams& p) {
   if (threadIdx.x == 0) {
     p.result->status = MB_ETIMEOUT;
+    p.result->epoch = p.epoch;
+    __threadfence_system();
+  }
+}
+
+// ---- K-A0 gate ---------------------------------------------------------------------------------------------------
+
+// One warp.  Lane t handles peer t: push my header into its block, release my flag there, wait for its flag here.
+__global__ void __launch_bounds__(32) ar_gate_kernel(const __grid_constant__ GateParams p) {
+  const int t = threadIdx.x;
+  const uint32_t par = p.epoch & 1u;
+  int fail = 0;
+  if (t < p.world && t != p.rank) {
+    volatile mb_ar_hdr* h = &p.sync[t]->ghdr[par][p.rank];
+    h->num_gradients = p.my_hdr.num_gradients;
+    h->num_skipped = p.my_hdr.num_skipped;
+    h->batch_size = p.my_hdr.batch_size;
+    h->has_grads = p.my_hdr.has_grads;
+    // release: the header stores above AND this stream's earlier kernels (the staged gradients) are visible to a
+    // peer that acquires the flag
+    st_release_sys_u32(&p.sync[t]->gate[p.rank], p.epoch);
+    if (!wait_flag(&p.sync[p.rank]->gate[t], p.epoch, p.timeout_ns, p.abort_flag)) fail = 1;
+    fence_acq_rel_sys();
+  }
+  fail = __any_sync(0xffffffffu, fail);
+  if (t != 0) return;
+  GateOut o;
+  o.tot = mb_ar_hdr{0, 0, 0, 0};
+  o.mask = 0;
+  o.epoch = p.epoch;
+  o.pad = 0;
+  if (fail) {
+    o.decision = 0;
+    *p.out = o;
+    p.result->status = MB_ETIMEOUT;
+    p.result->epoch = p.epoch;
+    __threadfence_system();
+    return;
+  }
+  for (int r = 0; r < p.world; ++r) {
+    uint64_t ng, ns, bs, hg;
+    if (r == p.rank) {
+      ng = p.my_hdr.num_gradients, ns = p.my_hdr.num_skipped, bs = p.my_hdr.batch_size, hg = p.my_hdr.has_grads;
+    } else {
+      const volatile mb_ar_hdr* ph = &p.sync[p.rank]->ghdr[par][r];
+      ng = ph->num_gradients, ns = ph->num_skipped, bs = ph->batch_size, hg = ph->has_grads;
+    }
+    o.tot.num_gradients += ng;
+    o.tot.num_skipped += ns;
+    o.tot.batch_size += bs;
+    if (hg) {
+      o.mask |= 1u << r;
+      o.tot.has_grads += 1;
+    }
+  }
+  o.decision = o.tot.batch_size >= p.min_batch ? 1 : 0;
+  *p.out = o;
+  if (!o.decision) {
+    // gate closed (src/accumulator.cc:1051: size < virtualBatchSize): nothing is reduced, the host counts again later
+    p.result->sum = o.tot;
+    p.result->status = MB_AR_SHORT;
     p.result->epoch = p.epoch;
     __threadfence_system();
   }
@@ -295,6 +418,30 @@ __device__ __forceinline__ void publish_header(const ArParams& p) {
     h->batch_size = p.my_hdr.batch_size;
     h->has_grads = p.my_hdr.has_grads;
   }
+}
+
+// Common prologue of the reduce kernels.  Ungated: publish header, per-block barrier with every peer, sum headers.
+// Gated: K-A0 already did all of that once for the whole GPU; read its verdict.  Returns false when the kernel must
+// return (barrier failure, or gate closed).
+__device__ __forceinline__ bool reduce_prologue(const ArParams& p, mb_ar_hdr* s_total, uint32_t* s_mask) {
+  if (p.gate) {
+    __shared__ int s_go;
+    if (threadIdx.x == 0) {
+      const GateOut g = *p.gate;
+      s_go = g.decision && g.epoch == p.epoch;
+      *s_total = g.tot;
+      *s_mask = g.mask;
+    }
+    __syncthreads();
+    return s_go != 0;
+  }
+  publish_header(p);
+  if (!block_barrier(p, false)) {
+    report_failure(p);
+    return false;
+  }
+  gather_headers(p, s_total, s_mask);
+  return true;
 }
 
 __device__ __forceinline__ float reduce_scale(const ArParams& p, const mb_ar_hdr& tot) {
@@ -368,20 +515,39 @@ __device__ __forceinline__ void write_result(const ArParams& p, const mb_ar_hdr&
   }
 }
 
+// Destination of the reduced vectors: the flat result buffer (ntensors == 0) or the tensor list.
+struct Sink {
+  TensorTable tb;
+  float* flat;
+  uint32_t cur;
+  __device__ __forceinline__ void put(uint64_t v, const float4& r) {
+    if (flat) st_f4(flat + v * 4, r);
+    else scatter_vec(tb, v, r, cur);
+  }
+};
+
+__device__ __forceinline__ Sink make_sink(const ArParams& p, uint8_t* smem) {
+  Sink s;
+  s.cur = 0;
+  if (p.ntensors == 0) {
+    s.flat = p.flat_dst;
+    s.tb = TensorTable{nullptr, nullptr, nullptr, 0};
+  } else {
+    s.flat = nullptr;
+    s.tb = load_table(smem, p.dst_tab, p.ntensors);
+  }
+  return s;
+}
+
 // ---- K-A2 one-shot ----------------------------------------------------------------------------------------------
 
 template <int NR>
 __global__ void __launch_bounds__(kArThreads, 1) ar_oneshot_kernel(const __grid_constant__ ArParams p) {
-  __shared__ uint32_t s_off[kArMaxTensors];
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ mb_ar_hdr s_total;
   __shared__ uint32_t s_mask;
-  load_offsets(s_off, p.dst_tab, p.ntensors);
-  publish_header(p);
-  if (!block_barrier(p, false)) {
-    report_failure(p);
-    return;
-  }
-  gather_headers(p, &s_total, &s_mask);
+  Sink sink = make_sink(p, dyn_smem);
+  if (!reduce_prologue(p, &s_total, &s_mask)) return;
   const uint32_t mask = s_mask;
   const mb_ar_hdr tot = s_total;
   const bool do_scale = p.scale && tot.num_gradients != 0;
@@ -399,14 +565,14 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_oneshot_kernel(const __grid_
       for (int k = 0; k < U; ++k) v[k] = base + (uint64_t)k * kArThreads + threadIdx.x;
       reduce_vecs<NR, U>(p.stage, mask, v, r);  // mask == 0 -> zeros (src/accumulator.cc:426-428)
 #pragma unroll
-      for (int k = 0; k < U; ++k) scatter_vec(p.dst_tab, s_off, p.ntensors, v[k], scale_vec(r[k], s, do_scale));
+      for (int k = 0; k < U; ++k) sink.put(v[k], scale_vec(r[k], s, do_scale));
     } else {
       const uint64_t cend = min(base + kChunk, p.total_vec);
       for (uint64_t v0 = base + threadIdx.x; v0 < cend; v0 += kArThreads) {
         uint64_t v[1] = {v0};
         float4 r[1];
         reduce_vecs<NR, 1>(p.stage, mask, v, r);
-        scatter_vec(p.dst_tab, s_off, p.ntensors, v0, scale_vec(r[0], s, do_scale));
+        sink.put(v0, scale_vec(r[0], s, do_scale));
       }
     }
   }
@@ -417,16 +583,11 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_oneshot_kernel(const __grid_
 
 template <int NR>
 __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_constant__ ArParams p) {
-  __shared__ uint32_t s_off[kArMaxTensors];
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ mb_ar_hdr s_total;
   __shared__ uint32_t s_mask;
-  load_offsets(s_off, p.dst_tab, p.ntensors);
-  publish_header(p);
-  if (!block_barrier(p, false)) {
-    report_failure(p);
-    return;
-  }
-  gather_headers(p, &s_total, &s_mask);
+  Sink sink = make_sink(p, dyn_smem);
+  if (!reduce_prologue(p, &s_total, &s_mask)) return;
   const uint32_t mask = s_mask;
   const mb_ar_hdr tot = s_total;
   const bool do_scale = p.scale && tot.num_gradients != 0;
@@ -434,8 +595,8 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
   constexpr int U = Unroll<NR>::value;
   constexpr uint64_t kChunk = (uint64_t)U * kArThreads;
   const uint64_t gstride = (uint64_t)gridDim.x * kChunk;
-  // phase 1: reduce my slice, write it to my destinations and into every peer's staging (in place: slice `rank` of a
-  // peer's staging is read only by me, and I overwrite an element only after I have loaded it).  Chunks are relative
+  // phase 1: reduce my slice and write it into every peer's staging (in place: slice `rank` of a peer's staging is
+  // read only by me, and I overwrite an element only after I have loaded it) and into my own.  Chunks are relative
   // to the slice start so that block b touches the same relative ranges of every slice on every rank.
   {
     const uint64_t sbase = (uint64_t)p.rank * p.slice_vec;
@@ -443,9 +604,7 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
     auto emit = [&](uint64_t v, const float4& red) {
       const float4 o = scale_vec(red, s, do_scale);
 #pragma unroll
-      for (int q = 0; q < NR; ++q)
-        if (q != p.rank) st_f4(p.stage[q] + v * 4, o);
-      scatter_vec(p.dst_tab, s_off, p.ntensors, v, o);
+      for (int q = 0; q < NR; ++q) st_f4(p.stage[q] + v * 4, o);
     };
     for (uint64_t cb = (uint64_t)blockIdx.x * kChunk; cb < slen; cb += gstride) {
       if (cb + kChunk <= slen && !p.force_u1) {
@@ -471,18 +630,24 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
     report_failure(p);
     return;
   }
-  // phase 2: the other slices are now complete in my own staging; block b reads exactly what the peers' block b wrote
+  // phase 2: every slice is now complete in my own staging (mine included, written by this same block before the
+  // barrier); block b reads exactly what the peers' block b wrote.  Slices ascend, so the sink's cursor only moves
+  // forward.
   float* mine = p.stage[p.rank];
 #pragma unroll 1
   for (int q = 0; q < NR; ++q) {
-    if (q == p.rank) continue;
     const uint64_t sbase = (uint64_t)q * p.slice_vec;
     const uint64_t slen = sbase < p.total_vec ? min(p.slice_vec, p.total_vec - sbase) : 0;
     for (uint64_t cb = (uint64_t)blockIdx.x * kChunk; cb < slen; cb += gstride) {
       const uint64_t cend = min(cb + kChunk, slen);
-      for (uint64_t j = cb + threadIdx.x; j < cend; j += kArThreads) {
-        const uint64_t v = sbase + j;
-        scatter_vec(p.dst_tab, s_off, p.ntensors, v, ld_peer_f4(mine + v * 4));
+      if (cb + kChunk <= slen) {
+        float4 x[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) x[k] = ld_peer_f4(mine + (sbase + cb + (uint64_t)k * kArThreads + threadIdx.x) * 4);
+#pragma unroll
+        for (int k = 0; k < U; ++k) sink.put(sbase + cb + (uint64_t)k * kArThreads + threadIdx.x, x[k]);
+      } else {
+        for (uint64_t j = cb + threadIdx.x; j < cend; j += kArThreads) sink.put(sbase + j, ld_peer_f4(mine + (sbase + j) * 4));
       }
     }
   }
@@ -512,35 +677,48 @@ ArKernel kernel_for(int world, bool twoshot) {
 
 // ---- host helpers ------------------------------------------------------------------------------------------------
 
-uint64_t flat_layout(const uint64_t* numel, int n, std::vector<TensorEnt>* out, const void* const* ptrs) {
+constexpr int kBufs = MB_AR_BUFS_PER_SLOT;
+
+uint64_t flat_layout(const uint64_t* numel, int n) {
   uint64_t off = 0;
-  if (out) out->resize(n);
-  for (int i = 0; i < n; ++i) {
-    if (out) (*out)[i] = TensorEnt{reinterpret_cast<uint64_t>(ptrs ? ptrs[i] : nullptr), off, numel[i]};
-    off += (numel[i] + 3) & ~3ull;
-  }
+  for (int i = 0; i < n; ++i) off += (numel[i] + 3) & ~3ull;
   return off;
 }
 
-// Upload a tensor table if it differs from what the device already holds.
-int sync_table(mb_ar_ctx* ctx, int which, const std::vector<TensorEnt>& tab, cudaStream_t stream) {
+// Bring the device copy of tensor table `which` up to date with (ptrs, numel).  The cached host copy is compared in
+// place (no allocation when nothing changed -- the steady state: the same .grad tensors every step).
+int sync_table(mb_ar_ctx* ctx, int which, const void* const* ptrs, const uint64_t* numel, int n, uint64_t* total_out,
+               cudaStream_t stream) {
   auto& cache = ctx->tab_host[which];
-  if (cache.size() == tab.size() &&
-      (tab.empty() || std::memcmp(cache.data(), tab.data(), tab.size() * sizeof(TensorEnt)) == 0))
-    return MB_OK;
-  cache = tab;
-  if (!tab.empty()) {
+  bool same = cache.size() == (size_t)n;
+  uint64_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    if (same) {
+      const TensorEnt& e = cache[i];
+      same = e.ptr == reinterpret_cast<uint64_t>(ptrs[i]) && e.numel == numel[i] && e.off == off;
+    }
+    off += (numel[i] + 3) & ~3ull;
+  }
+  *total_out = off;
+  if (same) return MB_OK;
+  cache.resize(n);
+  off = 0;
+  for (int i = 0; i < n; ++i) {
+    cache[i] = TensorEnt{reinterpret_cast<uint64_t>(ptrs[i]), off, numel[i]};
+    off += (numel[i] + 3) & ~3ull;
+  }
+  if (n > 0) {
     // pageable source: the runtime stages it before returning, and the copy is ordered on `stream` after any kernel
     // still reading the previous table
-    MB_CUDA(cudaMemcpyAsync(ctx->tab_dev[which], cache.data(), tab.size() * sizeof(TensorEnt),
-                            cudaMemcpyHostToDevice, stream));
+    MB_CUDA(cudaMemcpyAsync(ctx->tab_dev[which], cache.data(), (size_t)n * sizeof(TensorEnt), cudaMemcpyHostToDevice,
+                            stream));
   }
   return MB_OK;
 }
 
-float* slot_buffer(mb_ar_ctx* ctx, float* base, int slot) {
+float* ring_buffer(mb_ar_ctx* ctx, float* base, int slot, int ahead) {
   const uint64_t floats = ctx->max_bytes / 4;
-  return base + ((uint64_t)slot * 2 + (uint64_t)ctx->parity[slot]) * floats;
+  return base + ((uint64_t)slot * kBufs + (uint64_t)((ctx->parity[slot] + ahead) % kBufs)) * floats;
 }
 
 uint64_t env_u64(const char* name, uint64_t dflt) {
@@ -550,13 +728,145 @@ uint64_t env_u64(const char* name, uint64_t dflt) {
 }
 
 uint64_t twoshot_min_bytes(int world) {
-  // below this the single barrier of the one-shot kernel wins; above it the (N-1)x ingress dominates.
+  // below this the one-shot kernel (no mid barrier) wins; above it the (N-1)x ingress dominates.
   // MB_AR_TWOSHOT_MIN_BYTES overrides (measured crossovers are recorded in DESIGN.md).
   static const uint64_t forced = env_u64("MB_AR_TWOSHOT_MIN_BYTES", 0);
   if (forced) return forced;
   if (world <= 2) return ~0ull;  // two-shot moves the same bytes as one-shot at N=2
   if (world <= 4) return 4ull << 20;  // measured on 4 B200: 1 MB 32 vs 36 us, 4.4 MB 51 vs 50 us, 16 MB 114 vs 80 us
   return 1ull << 20;
+}
+
+std::mutex g_smem_mu;
+
+int ensure_dyn_smem(const void* fn, size_t bytes) {
+  if (bytes <= 48 * 1024) return MB_OK;
+  std::lock_guard<std::mutex> l(g_smem_mu);
+  MB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return MB_OK;
+}
+
+size_t table_bytes(uint32_t n) { return (size_t)n * (8 + 8 + 4); }
+
+// Shared by mb_ar_allreduce (ungated: in-kernel per-block barrier) and mb_ar_reduce_gated (K-A0 + barrier-free reduce).
+int launch_reduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* const* dst, const uint64_t* numel,
+                  int ntensors, float* flat_dst, uint64_t flat_numel, int scale, int algo, uint32_t timeout_ms,
+                  bool gated, uint64_t min_batch, cudaEvent_t mid_event, cudaStream_t stream) {
+  uint64_t total = 0;
+  uint32_t ntab = 0;
+  float* flat_sink = nullptr;
+  if (dst) {
+    MB_CHECK_ARG(numel != nullptr, "mb_ar_allreduce: numel is null");
+    MB_CHECK_ARG(ntensors >= 1 && ntensors <= kArMaxTensors, "mb_ar_allreduce: ntensors %d not in [1,%d]", ntensors,
+                 kArMaxTensors);
+    int rc = sync_table(ctx, 1, reinterpret_cast<const void* const*>(dst), numel, ntensors, &total, stream);
+    if (rc) return rc;
+    ntab = (uint32_t)ntensors;
+  } else {
+    MB_CHECK_ARG(flat_dst != nullptr, "mb_ar_allreduce: neither dst nor flat_dst given");
+    if ((flat_numel & 3u) == 0 && (reinterpret_cast<uintptr_t>(flat_dst) & 15u) == 0) {
+      // whole float4 vectors, vector-aligned: the kernel stores straight into it, no table
+      total = flat_numel;
+      flat_sink = flat_dst;
+    } else {
+      const void* ptr = flat_dst;
+      int rc = sync_table(ctx, 1, &ptr, &flat_numel, 1, &total, stream);
+      if (rc) return rc;
+      ntab = 1;
+    }
+  }
+  MB_CHECK_ARG(total * 4 <= ctx->max_bytes, "mb_ar_allreduce: %llu bytes exceed the context's max_bytes %llu",
+               (unsigned long long)(total * 4), (unsigned long long)ctx->max_bytes);
+  MB_CHECK_ARG(total < (1ull << 33), "mb_ar_allreduce: tensor list too large");
+  for (int r = 0; r < ctx->world; ++r) {
+    if (!ctx->imported[r]) {
+      set_error("mb_ar_allreduce: peer %d has not been imported", r);
+      return MB_ESTATE;
+    }
+  }
+  const uint64_t timeout_ns = (uint64_t)(timeout_ms ? timeout_ms : 30000u) * 1000000ull;
+  const uint32_t epoch = ++ctx->epoch;
+  int launches = 0;
+
+  if (gated && ctx->world == 1) {
+    // single member (src/group.h:738-741 short-circuit): the gate is a host-side comparison
+    if (my_hdr->batch_size < min_batch) {
+      HostResult* r = ctx->result_host + slot;
+      r->sum = *my_hdr;
+      r->sum.has_grads = my_hdr->has_grads ? 1 : 0;
+      r->status = MB_AR_SHORT;
+      r->epoch = epoch;
+      if (mid_event) MB_CUDA(cudaEventRecord(mid_event, stream));
+      return 0;
+    }
+    gated = false;  // the N=1 reduce kernel has no barrier to skip
+  }
+  if (gated) {
+    GateParams g;
+    std::memset(&g, 0, sizeof(g));
+    for (int r = 0; r < ctx->world; ++r) g.sync[r] = ctx->peer_sync[r];
+    g.out = ctx->gate_out + slot;
+    g.result = ctx->result_dev + slot;
+    g.abort_flag = ctx->abort_dev;
+    g.my_hdr = *my_hdr;
+    g.my_hdr.has_grads = my_hdr->has_grads ? 1 : 0;
+    g.min_batch = min_batch;
+    g.timeout_ns = timeout_ns;
+    g.epoch = epoch;
+    g.rank = ctx->rank;
+    g.world = ctx->world;
+    ar_gate_kernel<<<1, 32, 0, stream>>>(g);
+    MB_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  if (mid_event) MB_CUDA(cudaEventRecord(mid_event, stream));
+
+  ArParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int r = 0; r < ctx->world; ++r) {
+    p.stage[r] = ring_buffer(ctx, ctx->peer_staging[r], slot, 0);
+    p.sync[r] = ctx->peer_sync[r];
+  }
+  p.dst_tab = ctx->tab_dev[1];
+  p.flat_dst = flat_sink;
+  p.gate = gated ? ctx->gate_out + slot : nullptr;
+  p.ntensors = ntab;
+  p.epoch = epoch;
+  p.total_vec = total / 4;
+  p.slice_vec = (p.total_vec + ctx->world - 1) / ctx->world;
+  p.my_hdr = *my_hdr;
+  p.my_hdr.has_grads = my_hdr->has_grads ? 1 : 0;
+  p.rank = ctx->rank;
+  p.world = ctx->world;
+  p.scale = scale ? 1 : 0;
+  p.result = ctx->result_dev + slot;
+  p.abort_flag = ctx->abort_dev;
+  p.timeout_ns = timeout_ns;
+
+  bool twoshot = false;
+  if (ctx->world > 1) {
+    if (algo == MB_AR_ALGO_TWOSHOT) twoshot = true;
+    else if (algo == MB_AR_ALGO_AUTO) twoshot = total * 4 >= twoshot_min_bytes(ctx->world);
+  }
+  const int sms = sm_count(ctx->device);
+  if (sms <= 0) return MB_ECUDA;
+  const uint64_t work_vec = twoshot ? p.slice_vec : p.total_vec;
+  const uint64_t chunk = (uint64_t)kArThreads * (ctx->world >= 8 ? 2 : ctx->world >= 4 ? 4 : 8);  // Unroll<NR>
+  uint64_t want = (work_vec + chunk - 1) / chunk;
+  if (want == 0) want = 1;
+  // One CTA per SM: with two, the per-block barrier pairs (block b <-> block b on every peer) run in two waves that start
+  // at different times on different GPUs; measured on 2 B200: 8-64 MB rounds became bimodal (43 us vs 370 us).
+  static const uint64_t blocks_per_sm = env_u64("MB_AR_BLOCKS_PER_SM", 1);
+  static const uint64_t force_u1 = env_u64("MB_AR_FORCE_U1", 0);
+  p.force_u1 = (int32_t)force_u1;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, kArMaxBlocks));
+  ArKernel k = kernel_for(ctx->world, twoshot);
+  const size_t smem = table_bytes(ntab);
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(k), smem);
+  if (rc) return rc;
+  k<<<grid, kArThreads, smem, stream>>>(p);
+  MB_CUDA(cudaGetLastError());
+  return launches + 1;
 }
 
 }  // namespace
@@ -568,7 +878,7 @@ extern "C" {
 
 uint64_t mb_ar_flat_numel(const uint64_t* numel, int ntensors) {
   if (!numel || ntensors <= 0) return 0;
-  return flat_layout(numel, ntensors, nullptr, nullptr);
+  return flat_layout(numel, ntensors);
 }
 
 int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int nslots, mb_ar_ctx** out) {
@@ -598,7 +908,7 @@ int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int ns
     cudaError_t e__ = (expr);                                                         \
     if (e__ != cudaSuccess) return fail(cuda_fail(e__, #expr, __FILE__, __LINE__));   \
   } while (0)
-  const uint64_t staging_bytes = (ctx->max_bytes * 2 * (uint64_t)nslots + 255) & ~255ull;
+  const uint64_t staging_bytes = (ctx->max_bytes * kBufs * (uint64_t)nslots + 255) & ~255ull;
   ctx->sync_offset = staging_bytes;
   ctx->block_bytes = (staging_bytes + sizeof(SyncBlock) + (2ull << 20) - 1) & ~((2ull << 20) - 1);
   MB_TRY(cudaMalloc(&ctx->block, ctx->block_bytes));
@@ -612,6 +922,8 @@ int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int ns
   *ctx->abort_host = 0;
   MB_TRY(cudaHostGetDevicePointer(&ctx->abort_dev, ctx->abort_host, 0));
   for (int w = 0; w < 2; ++w) MB_TRY(cudaMalloc(&ctx->tab_dev[w], sizeof(TensorEnt) * kArMaxTensors));
+  MB_TRY(cudaMalloc(&ctx->gate_out, sizeof(GateOut) * MB_AR_MAX_SLOTS));
+  MB_TRY(cudaMemset(ctx->gate_out, 0, sizeof(GateOut) * MB_AR_MAX_SLOTS));
   MB_TRY(cudaDeviceSynchronize());
 #undef MB_TRY
   ctx->peer_staging[rank] = ctx->staging;
@@ -643,6 +955,7 @@ int mb_ar_ctx_destroy(mb_ar_ctx* ctx) {
   if (ctx->block) cudaFree(ctx->block);
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
   if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
+  if (ctx->gate_out) cudaFree(ctx->gate_out);
   for (int w = 0; w < 2; ++w)
     if (ctx->tab_dev[w]) cudaFree(ctx->tab_dev[w]);
   delete ctx;
@@ -750,6 +1063,7 @@ int mb_ar_ctx_reset(mb_ar_ctx* ctx, int new_rank, int new_world) {
   ctx->peer_sync[ctx->rank] = nullptr;
   close_peers(ctx);
   MB_CUDA(cudaMemset(ctx->sync, 0, sizeof(SyncBlock)));
+  MB_CUDA(cudaMemset(ctx->gate_out, 0, sizeof(GateOut) * MB_AR_MAX_SLOTS));
   MB_CUDA(cudaDeviceSynchronize());
   *ctx->abort_host = 0;
   ctx->epoch = 0;
@@ -762,9 +1076,19 @@ int mb_ar_ctx_reset(mb_ar_ctx* ctx, int new_rank, int new_world) {
   return MB_OK;
 }
 
-void* mb_ar_staging(mb_ar_ctx* ctx, int slot) {
-  if (!ctx || slot < 0 || slot >= ctx->nslots) return nullptr;
-  return slot_buffer(ctx, ctx->staging, slot);
+void* mb_ar_staging(mb_ar_ctx* ctx, int slot) { return mb_ar_buffer(ctx, slot, 0); }
+
+void* mb_ar_buffer(mb_ar_ctx* ctx, int slot, int ahead) {
+  if (!ctx || slot < 0 || slot >= ctx->nslots || ahead < 0 || ahead >= kBufs) return nullptr;
+  return ring_buffer(ctx, ctx->staging, slot, ahead);
+}
+
+int mb_ar_slot_advance(mb_ar_ctx* ctx, int slot) {
+  MB_CHECK_ARG(ctx != nullptr, "mb_ar_slot_advance: null ctx");
+  MB_CHECK_ARG(slot >= 0 && slot < ctx->nslots, "mb_ar_slot_advance: slot %d out of range", slot);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  ctx->parity[slot] = (ctx->parity[slot] + 1) % kBufs;
+  return MB_OK;
 }
 
 int mb_ar_world(mb_ar_ctx* ctx) { return ctx ? ctx->world : MB_EINVAL; }
@@ -785,15 +1109,14 @@ int mb_ar_stage(mb_ar_ctx* ctx, int slot, const float* const* grads, const uint6
   std::lock_guard<std::mutex> l(ctx->mu);
   DeviceGuard g(ctx->device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  std::vector<TensorEnt> tab;
-  const uint64_t total = flat_layout(numel, ntensors, &tab, reinterpret_cast<const void* const*>(grads));
+  uint64_t total = 0;
+  int rc = sync_table(ctx, 0, reinterpret_cast<const void* const*>(grads), numel, ntensors, &total, stream);
+  if (rc) return rc;
   MB_CHECK_ARG(total * 4 <= ctx->max_bytes, "mb_ar_stage: %llu bytes exceed the context's max_bytes %llu",
                (unsigned long long)(total * 4), (unsigned long long)ctx->max_bytes);
   if (total == 0) return 0;
-  int rc = sync_table(ctx, 0, tab, stream);
-  if (rc) return rc;
   StageParams p;
-  p.staging = slot_buffer(ctx, ctx->staging, slot);
+  p.staging = ring_buffer(ctx, ctx->staging, slot, 0);
   p.tab = ctx->tab_dev[0];
   p.ntensors = (uint32_t)ntensors;
   p.accumulate = accumulate;
@@ -803,7 +1126,10 @@ int mb_ar_stage(mb_ar_ctx* ctx, int slot, const float* const* grads, const uint6
   if (sms <= 0) return MB_ECUDA;
   const uint64_t want = (p.total_vec + kArThreads - 1) / kArThreads;
   const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)sms * 4);
-  ar_stage_kernel<<<grid, kArThreads, 0, stream>>>(p);
+  const size_t smem = table_bytes(p.ntensors);
+  rc = ensure_dyn_smem(reinterpret_cast<const void*>(ar_stage_kernel), smem);
+  if (rc) return rc;
+  ar_stage_kernel<<<grid, kArThreads, smem, stream>>>(p);
   MB_CUDA(cudaGetLastError());
   return 1;
 }
@@ -815,74 +1141,24 @@ int mb_ar_allreduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* co
   MB_CHECK_ARG(slot >= 0 && slot < ctx->nslots, "mb_ar_allreduce: slot %d out of range", slot);
   std::lock_guard<std::mutex> l(ctx->mu);
   DeviceGuard g(ctx->device);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  std::vector<TensorEnt> tab;
-  uint64_t total;
-  if (dst) {
-    MB_CHECK_ARG(numel != nullptr, "mb_ar_allreduce: numel is null");
-    MB_CHECK_ARG(ntensors >= 1 && ntensors <= kArMaxTensors, "mb_ar_allreduce: ntensors %d not in [1,%d]", ntensors,
-                 kArMaxTensors);
-    total = flat_layout(numel, ntensors, &tab, reinterpret_cast<const void* const*>(dst));
-  } else {
-    MB_CHECK_ARG(flat_dst != nullptr, "mb_ar_allreduce: neither dst nor flat_dst given");
-    const void* ptr = flat_dst;
-    total = flat_layout(&flat_numel, 1, &tab, &ptr);
-    ntensors = 1;
-  }
-  MB_CHECK_ARG(total * 4 <= ctx->max_bytes, "mb_ar_allreduce: %llu bytes exceed the context's max_bytes %llu",
-               (unsigned long long)(total * 4), (unsigned long long)ctx->max_bytes);
-  MB_CHECK_ARG(total < (1ull << 33), "mb_ar_allreduce: tensor list too large");
-  for (int r = 0; r < ctx->world; ++r) {
-    if (!ctx->imported[r]) {
-      set_error("mb_ar_allreduce: peer %d has not been imported", r);
-      return MB_ESTATE;
-    }
-  }
-  int rc = sync_table(ctx, 1, tab, stream);
-  if (rc) return rc;
+  int rc = launch_reduce(ctx, slot, my_hdr, dst, numel, ntensors, flat_dst, flat_numel, scale_by_num_gradients, algo,
+                         timeout_ms, /*gated=*/false, 0, nullptr, static_cast<cudaStream_t>(stream_));
+  // the next round on this slot stages into the next ring buffer: peers may still be reading this one
+  if (rc >= 0) ctx->parity[slot] = (ctx->parity[slot] + 1) % kBufs;
+  return rc;
+}
 
-  ArParams p;
-  std::memset(&p, 0, sizeof(p));
-  for (int r = 0; r < ctx->world; ++r) {
-    p.stage[r] = slot_buffer(ctx, ctx->peer_staging[r], slot);
-    p.sync[r] = ctx->peer_sync[r];
-  }
-  p.dst_tab = ctx->tab_dev[1];
-  p.ntensors = (uint32_t)ntensors;
-  p.epoch = ++ctx->epoch;
-  p.total_vec = total / 4;
-  p.slice_vec = (p.total_vec + ctx->world - 1) / ctx->world;
-  p.my_hdr = *my_hdr;
-  p.my_hdr.has_grads = my_hdr->has_grads ? 1 : 0;
-  p.rank = ctx->rank;
-  p.world = ctx->world;
-  p.scale = scale_by_num_gradients ? 1 : 0;
-  p.result = ctx->result_dev + slot;
-  p.abort_flag = ctx->abort_dev;
-  p.timeout_ns = (uint64_t)(timeout_ms ? timeout_ms : 30000u) * 1000000ull;
-  ctx->parity[slot] ^= 1;  // the next round on this slot stages into the other buffer (see header comment)
-
-  bool twoshot = false;
-  if (ctx->world > 1) {
-    if (algo == MB_AR_ALGO_TWOSHOT) twoshot = true;
-    else if (algo == MB_AR_ALGO_AUTO) twoshot = total * 4 >= twoshot_min_bytes(ctx->world);
-  }
-  const int sms = sm_count(ctx->device);
-  if (sms <= 0) return MB_ECUDA;
-  const uint64_t work_vec = twoshot ? p.slice_vec : p.total_vec;
-  const uint64_t chunk = (uint64_t)kArThreads * (ctx->world >= 8 ? 2 : ctx->world >= 4 ? 4 : 8);  // Unroll<NR>
-  uint64_t want = (work_vec + chunk - 1) / chunk;
-  if (want == 0) want = 1;
-  // One CTA per SM: with two, the per-block barrier pairs (block b <-> block b on every peer) run in two waves that start
-  // at different times on different GPUs; measured on 2 B200: 8-64 MB rounds became bimodal (43 us vs 370 us).
-  static const uint64_t blocks_per_sm = env_u64("MB_AR_BLOCKS_PER_SM", 1);
-  static const uint64_t force_u1 = env_u64("MB_AR_FORCE_U1", 0);
-  p.force_u1 = (int32_t)force_u1;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, kArMaxBlocks));
-  ArKernel k = kernel_for(ctx->world, twoshot);
-  k<<<grid, kArThreads, 0, stream>>>(p);
-  MB_CUDA(cudaGetLastError());
-  return 1;
+int mb_ar_reduce_gated(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, uint64_t min_batch_size, float* const* dst,
+                       const uint64_t* numel, int ntensors, float* flat_dst, uint64_t flat_numel,
+                       int scale_by_num_gradients, int algo, uint32_t timeout_ms, mb_event_t mid_event,
+                       mb_stream_t stream_) {
+  MB_CHECK_ARG(ctx && my_hdr, "mb_ar_reduce_gated: null argument");
+  MB_CHECK_ARG(slot >= 0 && slot < ctx->nslots, "mb_ar_reduce_gated: slot %d out of range", slot);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  DeviceGuard g(ctx->device);
+  return launch_reduce(ctx, slot, my_hdr, dst, numel, ntensors, flat_dst, flat_numel, scale_by_num_gradients, algo,
+                       timeout_ms, /*gated=*/true, min_batch_size, static_cast<cudaEvent_t>(mid_event),
+                       static_cast<cudaStream_t>(stream_));
 }
 
 int mb_ar_result(mb_ar_ctx* ctx, int slot, mb_ar_hdr* sum_out, int* status_out) {

@@ -65,6 +65,74 @@ def test_single_learner_accumulator_on_gpu():
     acc.zero_gradients()
     assert not acc.has_gradients() and not m.weight.grad.any().item()
 
+    # ---- zero-copy round: .grad now lives in the NVLink staging ring, a real backward() accumulates in place and
+    # reduce_gradients() launches no stage kernel (one launch in total: K-A2) ----
+    tm = acc.reduce_timings(clear=True)
+    assert tm["device_gate"] and tm["stage_launches"] == 2 and tm["zero_copy_rounds"] == 0
+    x = torch.from_numpy(gen_input(9, [20, 32], "f32")).cuda()
+    ref = torch.nn.Linear(32, 31).cuda()
+    ref.load_state_dict(m.state_dict())
+    before = _C.kernel_launches()
+    (m(x) ** 2).sum().backward()
+    (ref(x) ** 2).sum().backward()
+    gptr = m.weight.grad.data_ptr()
+    acc.reduce_gradients(20)
+    assert m.weight.grad.data_ptr() != gptr and not m.weight.grad.any().item()  # next ring buffer, zero-filled
+    t0 = time.time()
+    while not acc.has_gradients():
+        broker.update()
+        acc.update()
+        assert time.time() - t0 < 30
+    assert _C.kernel_launches() - before == 1
+    tm = acc.reduce_timings()
+    assert tm["zero_copy_rounds"] == 1 and tm["stage_launches"] == 0 and len(tm["reduce_us"]) == 1
+    assert torch.equal(m.weight.grad, ref.weight.grad) and torch.equal(m.bias.grad, ref.bias.grad)  # 1 gradient: x 1.0f
+    assert acc.model_version() == 2
+    # clip + optimizer step work on the result views; zero_gradients() goes back to the (zeroed) staging ring
+    torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    torch.optim.SGD(m.parameters(), lr=0.1).step()
+    acc.zero_gradients()
+    assert not m.weight.grad.any().item() and not m.bias.grad.any().item()
+
+
+def test_parallel_gradients_on_gpu():
+    """set_parallel_gradients(2) with CUDA parameters: the second slot is filled while the first is still in flight;
+    results are applied one by one in order and never mix (round-1 advisor finding)."""
+    addr = "127.0.0.1:47311"
+    broker = moolib.Broker()
+    broker.listen(addr)
+    m = torch.nn.Linear(32, 31).cuda()
+    acc = moolib.Accumulator("acc2", m.parameters(), m.buffers())
+    acc.set_parallel_gradients(2)
+    acc.set_virtual_batch_size(10)
+    acc.connect(addr)
+    t0 = time.time()
+    while not (acc.connected() and acc.wants_gradients()):
+        broker.update()
+        acc.update()
+        assert time.time() - t0 < 60
+    gs = [(gen_input(50 + 2 * k, [31, 32], "f32"), gen_input(51 + 2 * k, [31], "f32")) for k in range(6)]
+    fed = applied = 0
+    t0 = time.time()
+    while applied < 6:
+        assert time.time() - t0 < 60
+        broker.update()
+        acc.update()
+        if acc.has_gradients():
+            gw, gb = gs[applied]
+            assert m.weight.grad.cpu().numpy().tobytes() == gw.tobytes(), applied
+            assert m.bias.grad.cpu().numpy().tobytes() == gb.tobytes(), applied
+            acc.zero_gradients()
+            applied += 1
+        elif fed < 6 and acc.wants_gradients():
+            with torch.no_grad():
+                m.weight.grad.copy_(torch.from_numpy(gs[fed][0]))  # in place: into the slot's staging ring
+                m.bias.grad.copy_(torch.from_numpy(gs[fed][1]))
+            acc.reduce_gradients(10)
+            fed += 1
+    tm = acc.reduce_timings()
+    assert tm["zero_copy_rounds"] == 6 and tm["stage_launches"] == 0
+
 
 WORKER = r"""
 import os, sys, time, numpy as np, torch
@@ -108,13 +176,14 @@ for rnd in range(5):
     while not acc.wants_gradients():
         pump(); assert time.time() - t0 < 60
     skip = (rnd == 3 and rank == world - 1)
+    # the gate is evaluated on the device as part of reduce/skip_gradients(): set the virtual batch size first
+    acc.set_virtual_batch_size(10 * (world - 1) if rnd == 3 else 10 * world)
     if skip:
         acc.skip_gradients()
     else:
         m.weight.grad = torch.from_numpy(gen_input(100 * rnd + 2 * rank, [31, 32], 'f32')).cuda()
         m.bias.grad = torch.from_numpy(gen_input(100 * rnd + 2 * rank + 1, [31], 'f32')).cuda()
         acc.reduce_gradients(10)
-    acc.set_virtual_batch_size(10 * (world - 1) if rnd == 3 else 10 * world)
     t0 = time.time()
     while not acc.has_gradients():
         pump(); assert time.time() - t0 < 60, f'round {rnd}'
@@ -131,6 +200,39 @@ for rnd in range(5):
     s = acc.get_gradient_stats()
     assert (s['num_gradients'], s['num_skipped'], s['batch_size']) == eh[:3], (s, eh)
     acc.zero_gradients()
+# zero-copy rounds: gradients are written IN PLACE into .grad (views of the NVLink staging ring); round 6 needs two
+# contributions per rank before the device-side gate opens (the first attempt ends MB_AR_SHORT on every rank)
+acc.set_virtual_batch_size(10 * world)
+for rnd in range(5, 9):
+    need = 2 if rnd == 6 else 1
+    acc.set_virtual_batch_size(10 * world * need)
+    for c in range(need):
+        t0 = time.time()
+        while not acc.wants_gradients():
+            pump(); assert time.time() - t0 < 60
+        with torch.no_grad():
+            m.weight.grad.add_(torch.from_numpy(gen_input(100 * rnd + 2 * rank + 50 * c, [31, 32], 'f32')).cuda())
+            m.bias.grad.add_(torch.from_numpy(gen_input(100 * rnd + 2 * rank + 1 + 50 * c, [31], 'f32')).cuda())
+        acc.reduce_gradients(10)
+    t0 = time.time()
+    while not acc.has_gradients():
+        pump(); assert time.time() - t0 < 60, f'round {rnd}'
+    ins = []
+    for q in range(world):
+        f_ = np.zeros(total, dtype=np.float32)
+        for c in range(need):
+            g_ = np.zeros(total, dtype=np.float32)
+            g_[:992] = gen_input(100 * rnd + 2 * q + 50 * c, [992], 'f32'); g_[992:1023] = gen_input(100 * rnd + 2 * q + 1 + 50 * c, [31], 'f32')
+            oracle.stage(f_, [g_], accumulate=c > 0)
+        ins.append(f_)
+    exact, eh = oracle.allreduce_rankorder(ins, [(need, 0, 10 * need)] * world, numel=total)
+    assert m.weight.grad.cpu().numpy().reshape(-1).tobytes() == exact[:992].tobytes(), f'rank {rank} round {rnd}'
+    assert m.bias.grad.cpu().numpy().tobytes() == exact[992:1023].tobytes()
+    s = acc.get_gradient_stats()
+    assert (s['num_gradients'], s['num_skipped'], s['batch_size']) == eh[:3], (s, eh)
+    acc.zero_gradients()
+tm = acc.reduce_timings()
+assert tm['device_gate'] and tm['zero_copy_rounds'] >= 4 and tm['short_rounds'] >= 1, tm
 for _ in range(200):
     pump(); time.sleep(0.001)
 print(f'rank {rank} OK', flush=True)
