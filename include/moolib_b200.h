@@ -45,7 +45,6 @@ extern "C" {
 #define MB_AR_SHORT 1
 
 typedef void* mb_stream_t; /* cudaStream_t */
-typedef void* mb_event_t;  /* cudaEvent_t */
 
 MB_API int mb_version(void);
 MB_API const char* mb_last_error(void);
@@ -200,15 +199,17 @@ MB_API int mb_ar_allreduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, fl
  * MB_AR_SHORT + summed header when the gate was closed, MB_ETIMEOUT when a peer did not show up.  Every rank reaches the
  * same verdict (same headers, same min_batch_size).  The slot's ring does NOT advance: call mb_ar_slot_advance after MB_OK.
  * With world == 1 the gate is evaluated on the host and only K-A2 is launched (or nothing, when short).
- * `mid_event` (may be NULL) is recorded on `stream` between the two launches, so that a host that brackets the call with
- * its own events can tell the wait for the slowest peer (K-A0) from the data movement (K-A2).
+ * The context brackets the two launches with its own CUDA events: see mb_ar_round_times.
  * Returns the number of kernel launches.
  * (replaces: src/accumulator.cc:1035-1078 startCount -- an 8-byte allreduce over the RPC tree and one extra update() tick
  *  per step -- and :1005-1033 startReduce) */
 MB_API int mb_ar_reduce_gated(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, uint64_t min_batch_size,
                        float* const* dst, const uint64_t* numel, int ntensors, float* flat_dst, uint64_t flat_numel,
-                       int scale_by_num_gradients, int algo, uint32_t timeout_ms, mb_event_t mid_event,
-                       mb_stream_t stream);
+                       int scale_by_num_gradients, int algo, uint32_t timeout_ms, mb_stream_t stream);
+
+/* Device times of the most recent gated round on `slot`, once the stream has passed it: gate_us = K-A0 (includes the
+ * wait for the slowest peer), reduce_us = K-A2 (the data movement).  MB_ESTATE if the round launched no kernel. */
+MB_API int mb_ar_round_times(mb_ar_ctx* ctx, int slot, float* gate_us, float* reduce_us);
 
 /* Result of the most recent allreduce on `slot`: summed header and status (0 ok, MB_ETIMEOUT ...).  Reads pinned
  * host memory written by the kernel; only meaningful once the stream has reached the end of that allreduce

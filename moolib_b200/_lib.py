@@ -23,7 +23,7 @@ SYMBOLS = [
     "mb_copy2d_batch", "mb_gather_rows", "mb_stack_slot", "mb_cat_narrow", "mb_scatter_actions",
     "mb_ar_ctx_create", "mb_ar_ctx_destroy", "mb_ar_ctx_export", "mb_ar_ctx_import", "mb_ar_ctx_reset",
     "mb_ar_staging", "mb_ar_world", "mb_ar_rank", "mb_ar_stage", "mb_ar_allreduce", "mb_ar_result",
-    "mb_ar_flat_numel", "mb_ar_abort", "mb_ar_buffer", "mb_ar_slot_advance", "mb_ar_reduce_gated",
+    "mb_ar_flat_numel", "mb_ar_abort", "mb_ar_buffer", "mb_ar_slot_advance", "mb_ar_reduce_gated", "mb_ar_round_times",
 ]
 
 
@@ -92,7 +92,8 @@ def load():
     L.mb_ar_buffer.restype = vp
     L.mb_ar_slot_advance.argtypes = [vp, ci]
     L.mb_ar_reduce_gated.argtypes = [vp, ci, ctypes.POINTER(ArHdr), u64, ctypes.POINTER(vp), ctypes.POINTER(u64), ci, vp,
-                                     u64, ci, ci, u32, vp, vp]
+                                     u64, ci, ci, u32, vp]
+    L.mb_ar_round_times.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     _lib = L
     return L
 
@@ -254,10 +255,15 @@ class ArContext:
         if dst_tensors is not None:
             ptrs, numel, n = self._lists(dst_tensors)
             return check(self.L.mb_ar_reduce_gated(self._ctx, slot, ctypes.byref(h), min_batch, ptrs, numel, n, None, 0,
-                                                   int(scale), algo, timeout_ms, None, _stream_ptr(stream)))
+                                                   int(scale), algo, timeout_ms, _stream_ptr(stream)))
         return check(self.L.mb_ar_reduce_gated(self._ctx, slot, ctypes.byref(h), min_batch, None, None, 0,
                                                flat_dst.data_ptr(), flat_dst.numel(), int(scale), algo, timeout_ms,
-                                               None, _stream_ptr(stream)))
+                                               _stream_ptr(stream)))
+
+    def round_times(self, slot=0):
+        g, r = ctypes.c_float(), ctypes.c_float()
+        check(self.L.mb_ar_round_times(self._ctx, slot, ctypes.byref(g), ctypes.byref(r)))
+        return g.value, r.value
 
     def result(self, slot=0):
         h = ArHdr()

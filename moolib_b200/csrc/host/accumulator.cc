@@ -37,14 +37,13 @@ struct ReduceSlot {
   std::shared_ptr<SmallReduce> countOp;
   std::shared_ptr<SmallReduce> reduceOp;   // CPU-parameter path
   std::vector<torch::Tensor> cpuStaging;   // CPU-parameter path (src/accumulator.cc:847-874)
-  cudaEvent_t event = nullptr;             // device path: completion of the K-A2 launch (timing enabled)
+  cudaEvent_t event = nullptr;             // device path: completion of the K-A2 launch
   cudaEvent_t staged = nullptr;            // device path: this slot's gradients are complete (compute stream)
-  cudaEvent_t evBegin = nullptr, evMid = nullptr;  // device gate: before K-A0 / between K-A0 and K-A2 (timing)
   bool kernelInFlight = false;
   bool gated = false;                      // the in-flight launch is K-A0 + K-A2 (mb_ar_reduce_gated)
   Clock::time_point reduceStart;
   ~ReduceSlot() {
-    for (cudaEvent_t e : {event, staged, evBegin, evMid})
+    for (cudaEvent_t e : {event, staged})
       if (e) cudaEventDestroy(e);
   }
 };
@@ -406,8 +405,6 @@ class Accumulator {
       if (target) {  // keep the CUDA events (creating four per round costs more than the gate kernel)
         std::swap(fresh->event, target->event);
         std::swap(fresh->staged, target->staged);
-        std::swap(fresh->evBegin, target->evBegin);
-        std::swap(fresh->evMid, target->evMid);
       }
       target = slots_[index] = fresh;
       target->index = index;
@@ -490,16 +487,14 @@ class Accumulator {
     GradArena& a = arena();
     cudaStream_t stream = reduceStream();
     if (target->staged) cudaStreamWaitEvent(stream, target->staged, 0);
-    for (cudaEvent_t* e : {&target->evBegin, &target->evMid, &target->event})
-      if (!*e) cudaEventCreate(e);
-    cudaEventRecord(target->evBegin, stream);
+    if (!target->event) cudaEventCreateWithFlags(&target->event, cudaEventDisableTiming);
     target->isCounting = true;
     target->gated = true;
     target->reduceStart = Clock::now();
     launch_counter() += check(
         mb_ar_reduce_gated(reducer()->ctx(), (int)target->index, &target->data, virtualBatchSize_, nullptr, nullptr, 0,
                            a.result[target->index].data_ptr<float>(), (uint64_t)a.total, /*scale=*/1, MB_AR_ALGO_AUTO,
-                           (uint32_t)(parts_.rpc->getTimeout() * 1000), target->evMid, static_cast<mb_stream_t>(stream)),
+                           (uint32_t)(parts_.rpc->getTimeout() * 1000), static_cast<mb_stream_t>(stream)),
         "Accumulator gated allreduce");
     cudaEventRecord(target->event, stream);
     target->kernelInFlight = true;
@@ -551,7 +546,7 @@ class Accumulator {
                           nullptr, 0, /*scale=*/1, MB_AR_ALGO_AUTO, (uint32_t)(parts_.rpc->getTimeout() * 1000),
                           static_cast<mb_stream_t>(stream)),
           "Accumulator allreduce");
-      if (!target->event) cudaEventCreate(&target->event);
+      if (!target->event) cudaEventCreateWithFlags(&target->event, cudaEventDisableTiming);
       cudaEventRecord(target->event, stream);
       target->kernelInFlight = true;
       target->gated = false;
@@ -1019,15 +1014,10 @@ class Accumulator {
 
   // ---- device-side round timings (bench.py: roofline_nvlink) -------------------------------------------------------
   void recordTiming(ReduceSlot& v, bool reduced) {
-    float gateMs = 0.f, reduceMs = 0.f;
-    if (!v.evBegin || !v.evMid || !v.event) return;
-    if (cudaEventElapsedTime(&gateMs, v.evBegin, v.evMid) != cudaSuccess ||
-        cudaEventElapsedTime(&reduceMs, v.evMid, v.event) != cudaSuccess) {
-      cudaGetLastError();
-      return;
-    }
+    float gateUs = 0.f, reduceUs = 0.f;
+    if (mb_ar_round_times(reducer()->ctx(), (int)v.index, &gateUs, &reduceUs) != MB_OK) return;  // no kernel ran
     if (timings_.size() >= 65536) return;
-    timings_.push_back({gateMs * 1e3f, reduceMs * 1e3f, reduced});
+    timings_.push_back({gateUs, reduceUs, reduced});
   }
   py::dict reduceTimings(bool clear) {
     std::lock_guard<std::mutex> l(mu_);

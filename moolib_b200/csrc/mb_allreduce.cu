@@ -122,6 +122,8 @@ struct mb_ar_ctx {
   uint32_t* abort_host = nullptr;
   uint32_t* abort_dev = nullptr;
   mb::GateOut* gate_out = nullptr;   // device, one per slot
+  cudaEvent_t ev[MB_AR_MAX_SLOTS][3] = {};  // gated rounds: before K-A0 / between K-A0 and K-A2 / after K-A2 (timing)
+  bool ev_valid[MB_AR_MAX_SLOTS] = {};
   mb::TensorEnt* tab_dev[2] = {nullptr, nullptr};  // 0: stage sources, 1: allreduce destinations
   std::vector<mb::TensorEnt> tab_host[2];
   std::mutex mu;
@@ -751,10 +753,11 @@ size_t table_bytes(uint32_t n) { return (size_t)n * (8 + 8 + 4); }
 // Shared by mb_ar_allreduce (ungated: in-kernel per-block barrier) and mb_ar_reduce_gated (K-A0 + barrier-free reduce).
 int launch_reduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* const* dst, const uint64_t* numel,
                   int ntensors, float* flat_dst, uint64_t flat_numel, int scale, int algo, uint32_t timeout_ms,
-                  bool gated, uint64_t min_batch, cudaEvent_t mid_event, cudaStream_t stream) {
+                  bool gated, uint64_t min_batch, cudaStream_t stream) {
   uint64_t total = 0;
   uint32_t ntab = 0;
   float* flat_sink = nullptr;
+  const bool timed_round = gated;
   if (dst) {
     MB_CHECK_ARG(numel != nullptr, "mb_ar_allreduce: numel is null");
     MB_CHECK_ARG(ntensors >= 1 && ntensors <= kArMaxTensors, "mb_ar_allreduce: ntensors %d not in [1,%d]", ntensors,
@@ -796,11 +799,15 @@ int launch_reduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* cons
       r->sum.has_grads = my_hdr->has_grads ? 1 : 0;
       r->status = MB_AR_SHORT;
       r->epoch = epoch;
-      if (mid_event) MB_CUDA(cudaEventRecord(mid_event, stream));
+      ctx->ev_valid[slot] = false;
       return 0;
     }
     gated = false;  // the N=1 reduce kernel has no barrier to skip
   }
+  // the context's own events bracket the two launches of a gated round (mb_ar_round_times): the wait for the slowest
+  // peer (K-A0) and the data movement (K-A2) are told apart without the host handing event handles across the ABI
+  const bool timed = timed_round;
+  if (timed) MB_CUDA(cudaEventRecord(ctx->ev[slot][0], stream));
   if (gated) {
     GateParams g;
     std::memset(&g, 0, sizeof(g));
@@ -819,7 +826,7 @@ int launch_reduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* cons
     MB_CUDA(cudaGetLastError());
     ++launches;
   }
-  if (mid_event) MB_CUDA(cudaEventRecord(mid_event, stream));
+  if (timed) MB_CUDA(cudaEventRecord(ctx->ev[slot][1], stream));
 
   ArParams p;
   std::memset(&p, 0, sizeof(p));
@@ -866,6 +873,10 @@ int launch_reduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* cons
   if (rc) return rc;
   k<<<grid, kArThreads, smem, stream>>>(p);
   MB_CUDA(cudaGetLastError());
+  if (timed) {
+    MB_CUDA(cudaEventRecord(ctx->ev[slot][2], stream));
+    ctx->ev_valid[slot] = true;
+  }
   return launches + 1;
 }
 
@@ -922,6 +933,8 @@ int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int ns
   *ctx->abort_host = 0;
   MB_TRY(cudaHostGetDevicePointer(&ctx->abort_dev, ctx->abort_host, 0));
   for (int w = 0; w < 2; ++w) MB_TRY(cudaMalloc(&ctx->tab_dev[w], sizeof(TensorEnt) * kArMaxTensors));
+  for (int sl = 0; sl < MB_AR_MAX_SLOTS; ++sl)
+    for (int k = 0; k < 3; ++k) MB_TRY(cudaEventCreate(&ctx->ev[sl][k]));
   MB_TRY(cudaMalloc(&ctx->gate_out, sizeof(GateOut) * MB_AR_MAX_SLOTS));
   MB_TRY(cudaMemset(ctx->gate_out, 0, sizeof(GateOut) * MB_AR_MAX_SLOTS));
   MB_TRY(cudaDeviceSynchronize());
@@ -956,6 +969,9 @@ int mb_ar_ctx_destroy(mb_ar_ctx* ctx) {
   if (ctx->result_host) cudaFreeHost(ctx->result_host);
   if (ctx->abort_host) cudaFreeHost(ctx->abort_host);
   if (ctx->gate_out) cudaFree(ctx->gate_out);
+  for (int sl = 0; sl < MB_AR_MAX_SLOTS; ++sl)
+    for (int k = 0; k < 3; ++k)
+      if (ctx->ev[sl][k]) cudaEventDestroy(ctx->ev[sl][k]);
   for (int w = 0; w < 2; ++w)
     if (ctx->tab_dev[w]) cudaFree(ctx->tab_dev[w]);
   delete ctx;
@@ -1142,7 +1158,7 @@ int mb_ar_allreduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* co
   std::lock_guard<std::mutex> l(ctx->mu);
   DeviceGuard g(ctx->device);
   int rc = launch_reduce(ctx, slot, my_hdr, dst, numel, ntensors, flat_dst, flat_numel, scale_by_num_gradients, algo,
-                         timeout_ms, /*gated=*/false, 0, nullptr, static_cast<cudaStream_t>(stream_));
+                         timeout_ms, /*gated=*/false, 0, static_cast<cudaStream_t>(stream_));
   // the next round on this slot stages into the next ring buffer: peers may still be reading this one
   if (rc >= 0) ctx->parity[slot] = (ctx->parity[slot] + 1) % kBufs;
   return rc;
@@ -1150,15 +1166,30 @@ int mb_ar_allreduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* co
 
 int mb_ar_reduce_gated(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, uint64_t min_batch_size, float* const* dst,
                        const uint64_t* numel, int ntensors, float* flat_dst, uint64_t flat_numel,
-                       int scale_by_num_gradients, int algo, uint32_t timeout_ms, mb_event_t mid_event,
-                       mb_stream_t stream_) {
+                       int scale_by_num_gradients, int algo, uint32_t timeout_ms, mb_stream_t stream_) {
   MB_CHECK_ARG(ctx && my_hdr, "mb_ar_reduce_gated: null argument");
   MB_CHECK_ARG(slot >= 0 && slot < ctx->nslots, "mb_ar_reduce_gated: slot %d out of range", slot);
   std::lock_guard<std::mutex> l(ctx->mu);
   DeviceGuard g(ctx->device);
   return launch_reduce(ctx, slot, my_hdr, dst, numel, ntensors, flat_dst, flat_numel, scale_by_num_gradients, algo,
-                       timeout_ms, /*gated=*/true, min_batch_size, static_cast<cudaEvent_t>(mid_event),
-                       static_cast<cudaStream_t>(stream_));
+                       timeout_ms, /*gated=*/true, min_batch_size, static_cast<cudaStream_t>(stream_));
+}
+
+int mb_ar_round_times(mb_ar_ctx* ctx, int slot, float* gate_us, float* reduce_us) {
+  MB_CHECK_ARG(ctx != nullptr, "mb_ar_round_times: null ctx");
+  MB_CHECK_ARG(slot >= 0 && slot < ctx->nslots, "mb_ar_round_times: slot %d out of range", slot);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  if (!ctx->ev_valid[slot]) {
+    set_error("mb_ar_round_times: no timed round on slot %d", slot);
+    return MB_ESTATE;
+  }
+  DeviceGuard g(ctx->device);
+  float a = 0.f, b = 0.f;
+  MB_CUDA(cudaEventElapsedTime(&a, ctx->ev[slot][0], ctx->ev[slot][1]));
+  MB_CUDA(cudaEventElapsedTime(&b, ctx->ev[slot][1], ctx->ev[slot][2]));
+  if (gate_us) *gate_us = a * 1e3f;
+  if (reduce_us) *reduce_us = b * 1e3f;
+  return MB_OK;
 }
 
 int mb_ar_result(mb_ar_ctx* ctx, int slot, mb_ar_hdr* sum_out, int* status_out) {
