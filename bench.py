@@ -120,16 +120,16 @@ class BatchOpTimer:
                 n += x.numel() * x.element_size()
         return n
 
-    def batch_op(self, op, batcher, item):
+    def batch_op(self, op, fn, item, items_moved=1):
         if not self.enabled:
-            getattr(batcher, op)(item)
+            fn(item)
             return
         s, e = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
         l0 = self.kernel_launches()
         s.record()
-        getattr(batcher, op)(item)
+        fn(item)
         e.record()
-        self.records.append((op, s, e, self.payload(item), self.kernel_launches() - l0))
+        self.records.append((op, s, e, self.payload(item) * items_moved, self.kernel_launches() - l0))
 
     def summary(self, hbm_gbs, peak_kind):
         by = {}

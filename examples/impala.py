@@ -118,6 +118,7 @@ class Flags:
     read_metrics: bool = True         # True: grad-norm .item() per optimizer step, as experiment.py:166 does
     obs_pool: int = 8                 # distinct pre-generated observation slabs per buffer (defeats caching)
     max_queued_batches: int = 8       # back-pressure on the actor side: one time batch ahead (8 x 19 MB)
+    fused_batcher: bool = True        # moolib_b200 only: UnrollBatcher (stack x T fused with cat, one launch per unroll)
     seed: int = 1234
 
 
@@ -211,6 +212,12 @@ class LearnerLoop:
         class EnvState:
             pass
 
+        # moolib_b200 extensions, used when the API module has them (the reference module does not):
+        #   UnrollBatcher = Batcher(T).stack x T fused with Batcher(batch_size, dim=1).cat, one launch per unroll;
+        #   to_device     = EnvStepperFuture.result(device=...): all keys of a pinned result in one launch.
+        self.fused = bool(flags.fused_batcher and hasattr(api, "UnrollBatcher"))
+        self.to_device = getattr(api, "to_device", None)
+        self.T = T
         self.env_states = []
         for _ in range(flags.num_actor_batches):
             s = EnvState()
@@ -218,9 +225,15 @@ class LearnerLoop:
             s.prev_action = torch.zeros(B, dtype=torch.int64, device=self.device)
             s.core_state = ()
             s.initial_core_state = ()
-            s.time_batcher = api.Batcher(T, flags.device)
+            s.count = 0
+            if self.fused:
+                s.unroll = api.UnrollBatcher(T, flags.batch_size, flags.device, cat_dim=1)
+            else:
+                s.time_batcher = api.Batcher(T, flags.device)
             self.env_states.append(s)
         self.learn_batcher = api.Batcher(flags.batch_size, flags.device, dim=1)
+        self.learn_sources = [s.unroll for s in self.env_states] if self.fused else [self.learn_batcher]
+        self._next_source = 0
         self.res = LearnerResult()
         self.next_env_index = 0
         self.grad_norm_dev = torch.zeros((), device=self.device)
@@ -232,7 +245,7 @@ class LearnerLoop:
         if _DEBUG and time.time() - self._last_dbg > 5 and hasattr(acc, "debug_state"):
             self._last_dbg = time.time()
             print(f"[dbg pid {os.getpid()}] steps={self.res.optimizer_steps} actor={self.res.actor_steps} "
-                  f"queued={self.learn_batcher.size()} connected={acc.connected()} wants={acc.wants_gradients()} "
+                  f"queued={self.learn_size()} connected={acc.connected()} wants={acc.wants_gradients()} "
                   f"{acc.debug_state()}", file=sys.stderr, flush=True)
         if self.broker is not None:
             self.broker.update()
@@ -262,8 +275,8 @@ class LearnerLoop:
             self.res.optimizer_steps += 1
             self.res.t_opt += time.perf_counter() - t_tick
             return True
-        if not self.learn_batcher.empty() and acc.wants_gradients():
-            self.res.last_loss = compute_gradients(model, self.learn_batcher.get(), flags)
+        if self.learn_size() and acc.wants_gradients():
+            self.res.last_loss = compute_gradients(model, self.learn_get(), flags)
             self.res.env_train_steps += flags.unroll_length * flags.batch_size
             acc.reduce_gradients(flags.batch_size)
             self.res.n_learn += 1
@@ -272,7 +285,7 @@ class LearnerLoop:
         if acc.wants_gradients():
             acc.skip_gradients()
             self.res.n_skip += 1
-        if self.learn_batcher.size() >= self.flags.max_queued_batches:
+        if self.learn_size() >= self.flags.max_queued_batches:
             # (not in the reference loop) never let unconsumed learner batches pile up in device memory while the
             # accumulator is not asking for gradients
             time.sleep(0.0002)
@@ -285,7 +298,10 @@ class LearnerLoop:
         if es.future is None:
             es.future = self.envs.step(cur, es.prev_action)
         cpu_env_outputs = es.future.result()
-        env_outputs = {k: v.to(self.device, copy=True, non_blocking=True) for k, v in cpu_env_outputs.items()}
+        if self.to_device is not None:
+            env_outputs = self.to_device(cpu_env_outputs, flags.device)  # one launch for all keys (pinned slabs)
+        else:
+            env_outputs = {k: v.to(self.device, copy=True, non_blocking=True) for k, v in cpu_env_outputs.items()}
         env_outputs["prev_action"] = es.prev_action
         prev_core_state = es.core_state
         model.eval()
@@ -298,27 +314,46 @@ class LearnerLoop:
         es.future = self.envs.step(cur, action)
         self.res.actor_steps += 1
         last_data = {"env_outputs": env_outputs, "actor_outputs": actor_outputs}
-        self._stack(es.time_batcher, last_data)
-        if not es.time_batcher.empty():
-            data = es.time_batcher.get()
-            data["initial_core_state"] = es.initial_core_state
-            self._cat(self.learn_batcher, data)
-            es.initial_core_state = prev_core_state
-            self._stack(es.time_batcher, last_data)
+        if self.fused:
+            es.count += 1
+            if es.count == self.T:
+                # this item completes the unroll: [T, B, ...] is gathered straight into B/32 learner batches
+                es.unroll.set_extra("initial_core_state", es.initial_core_state)
+                self._op("unroll_gather", es.unroll.stack, last_data, self.T)
+                es.initial_core_state = prev_core_state
+                es.unroll.stack(last_data)
+                es.count = 1
+            else:
+                es.unroll.stack(last_data)  # retained, no copy
+        else:
+            self._op("stack", es.time_batcher.stack, last_data, 1)
+            if not es.time_batcher.empty():
+                data = es.time_batcher.get()
+                data["initial_core_state"] = es.initial_core_state
+                self._op("cat", self.learn_batcher.cat, data, 1)
+                es.initial_core_state = prev_core_state
+                self._op("stack", es.time_batcher.stack, last_data, 1)
         self.res.t_act += time.perf_counter() - t_tick
         return False
 
-    def _stack(self, batcher, item):
-        if self.hooks is not None:
-            self.hooks.batch_op("stack", batcher, item)
-        else:
-            batcher.stack(item)
+    def learn_size(self):
+        return sum(b.size() for b in self.learn_sources)
 
-    def _cat(self, batcher, item):
+    def learn_get(self):
+        for _ in range(len(self.learn_sources)):
+            b = self.learn_sources[self._next_source]
+            self._next_source = (self._next_source + 1) % len(self.learn_sources)
+            if not b.empty():
+                return b.get()
+        raise RuntimeError("learn_get() without a queued learner batch")
+
+    def _op(self, name, fn, item, items_moved):
+        """Run one Batcher call; bench.py's hooks time it with CUDA events (items_moved = how many items' payload the
+        call moves: an UnrollBatcher gather moves the whole unroll)."""
         if self.hooks is not None:
-            self.hooks.batch_op("cat", batcher, item)
+            self.hooks.batch_op(name, fn, item, items_moved)
         else:
-            batcher.cat(item)
+            fn(item)
 
     def finish(self):
         if not self.flags.read_metrics:

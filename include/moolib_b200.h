@@ -82,6 +82,24 @@ typedef struct mb_copy_job {
  * (>= 0) or a negative error. */
 MB_API int mb_copy2d_batch(const mb_copy_job* jobs, int njobs, mb_stream_t stream);
 
+/* Where the sources of a table live.  DEVICE / HOST_MAPPED is the caller's promise for EVERY job of the call (the host
+ * layer knows: tensor.is_cuda() vs a pinned slab) and saves one driver query per bulk job; UNKNOWN asks the driver. */
+#define MB_SRC_UNKNOWN 0
+#define MB_SRC_DEVICE 1
+#define MB_SRC_HOST_MAPPED 2 /* PCIe-bound: the launch is limited to a few dozen CTAs so the SMs stay free */
+MB_API int mb_copy2d_batch_ex(const mb_copy_job* jobs, int njobs, int src_kind, mb_stream_t stream);
+
+/* Tables of ANY length in ONE launch: the normalised table is written into pinned staging owned by the context,
+ * uploaded with one async copy and read by the kernels from device memory (tables of <= MB_COPY_MAX_INLINE_JOBS jobs
+ * still travel in the kernel parameters, no upload).  This is what lets a whole unroll -- T time steps x leaves x
+ * learner batches, ~1200 pitched copies -- be gathered straight into its final layout by one kernel instead of T stack
+ * launches followed by a re-tiling pass.  max_jobs bounds one launch; longer tables are split.
+ * (replaces: src/moolib.cc:813-845 stack x T followed by :767-811 cat, i.e. two passes over every observation byte) */
+typedef struct mb_copy_ctx mb_copy_ctx;
+MB_API int mb_copy_ctx_create(int device, uint32_t max_jobs, mb_copy_ctx** out);
+MB_API int mb_copy_ctx_destroy(mb_copy_ctx* ctx);
+MB_API int mb_copy2d_table(mb_copy_ctx* ctx, const mb_copy_job* jobs, int njobs, int src_kind, mb_stream_t stream);
+
 /* K-B1/K-B4: gather `nrows` rows of `row_bytes` from the pointers in the DEVICE array `src_rows_dev` into
  * dst + i*dst_pitch.  (replaces: src/env.h:258 per-env memcpy + experiment.py:492 H2D; src/batch_utils.cc:295) */
 MB_API int mb_gather_rows(void* dst, uint64_t dst_pitch, const void* const* src_rows_dev, uint64_t row_bytes,

@@ -16,11 +16,13 @@ MB_AR_MAX_SLOTS = 4
 MB_AR_BUFS_PER_SLOT = 3
 MB_AR_SHORT = 1
 MB_COPY_MAX_INLINE_JOBS = 64
+MB_SRC_UNKNOWN, MB_SRC_DEVICE, MB_SRC_HOST_MAPPED = 0, 1, 2
 
 # every symbol include/moolib_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "mb_version", "mb_last_error", "mb_sm_count",
-    "mb_copy2d_batch", "mb_gather_rows", "mb_stack_slot", "mb_cat_narrow", "mb_scatter_actions",
+    "mb_copy2d_batch", "mb_copy2d_batch_ex", "mb_copy_ctx_create", "mb_copy_ctx_destroy", "mb_copy2d_table",
+    "mb_gather_rows", "mb_stack_slot", "mb_cat_narrow", "mb_scatter_actions",
     "mb_ar_ctx_create", "mb_ar_ctx_destroy", "mb_ar_ctx_export", "mb_ar_ctx_import", "mb_ar_ctx_reset",
     "mb_ar_staging", "mb_ar_world", "mb_ar_rank", "mb_ar_stage", "mb_ar_allreduce", "mb_ar_result",
     "mb_ar_flat_numel", "mb_ar_abort", "mb_ar_buffer", "mb_ar_slot_advance", "mb_ar_reduce_gated", "mb_ar_round_times",
@@ -68,6 +70,10 @@ def load():
     L.mb_last_error.restype = ctypes.c_char_p
     L.mb_sm_count.argtypes = [ci]
     L.mb_copy2d_batch.argtypes = [ctypes.POINTER(CopyJob), ci, vp]
+    L.mb_copy2d_batch_ex.argtypes = [ctypes.POINTER(CopyJob), ci, ci, vp]
+    L.mb_copy_ctx_create.argtypes = [ci, u32, ctypes.POINTER(vp)]
+    L.mb_copy_ctx_destroy.argtypes = [vp]
+    L.mb_copy2d_table.argtypes = [vp, ctypes.POINTER(CopyJob), ci, ci, vp]
     L.mb_gather_rows.argtypes = [vp, u64, vp, u64, u64, vp]
     L.mb_stack_slot.argtypes = [vp, u64, u64, u64, u64, vp, vp]
     L.mb_cat_narrow.argtypes = [vp, vp, u64, u64, u64, u64, u64, u64, u64, vp]
@@ -129,6 +135,30 @@ def make_jobs(jobs):
 def copy2d_batch(jobs, stream=None):
     arr = jobs if isinstance(jobs, ctypes.Array) else make_jobs(list(jobs))
     return check(load().mb_copy2d_batch(arr, len(arr), _stream_ptr(stream)))
+
+
+class CopyContext:
+    """Staging for device-resident job tables (mb_copy_ctx): any number of pitched copies in one launch."""
+
+    def __init__(self, device, max_jobs=8192):
+        self.L = load()
+        self._ctx = ctypes.c_void_p()
+        check(self.L.mb_copy_ctx_create(device, max_jobs, ctypes.byref(self._ctx)))
+
+    def close(self):
+        if self._ctx:
+            self.L.mb_copy_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def copy(self, jobs, src_kind=MB_SRC_UNKNOWN, stream=None):
+        arr = jobs if isinstance(jobs, ctypes.Array) else make_jobs(list(jobs))
+        return check(self.L.mb_copy2d_table(self._ctx, arr, len(arr), src_kind, _stream_ptr(stream)))
 
 
 def stack_slot(dst, slot, src, dim=0, stream=None):

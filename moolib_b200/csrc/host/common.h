@@ -66,6 +66,8 @@ void unhandleAll(Rpc& rpc, std::initializer_list<std::string> names) {
 // utils::stackFields / unstackFields (reference: src/batch_utils.cc:259-325), implemented in batcher.cc
 py::object stackFields(const py::tuple& input, int64_t dim);
 py::tuple unstackFields(const py::handle& input, int64_t batchSize, int64_t dim);
+// every tensor of a nest on `device`; pinned host tensors are read by one launch of the copy kernel (batcher.cc)
+py::object nestToDevice(const py::handle& nest, const std::string& device);
 
 void bind_batcher(py::module_& m);
 void bind_accumulator(py::module_& m);

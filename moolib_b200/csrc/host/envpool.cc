@@ -17,6 +17,8 @@
 // Process management is deliberately simpler than the reference's double-fork server (src/env.cc:176-223): the
 // workers are forked directly in the constructor.
 #include "common.h"
+
+#include <optional>
 #include "control.h"
 
 #include <fcntl.h>
@@ -250,7 +252,10 @@ struct EnvStepperFuture {
   std::shared_ptr<void> keep;
   int bufferIndex;
   size_t size, stride;
-  py::object result();
+  // device = None: CPU tensors aliasing the (pinned, device-mapped) slabs, as the reference (src/env.cc:389-401).
+  // device = "cuda:i": every key on the device, read from the slabs by ONE launch of the copy kernel -- what the actor
+  // loop otherwise does with one `.to(device)` per key (examples/vtrace/experiment.py:492-494).
+  py::object result(std::optional<std::string> device);
 };
 
 class EnvStepper : public std::enable_shared_from_this<EnvStepper> {
@@ -440,10 +445,14 @@ class EnvStepper : public std::enable_shared_from_this<EnvStepper> {
   std::vector<void*> registered_;
 };
 
-py::object EnvStepperFuture::result() { return stepper->result(bufferIndex, size, stride); }
+py::object EnvStepperFuture::result(std::optional<std::string> device) {
+  py::object host = stepper->result(bufferIndex, size, stride);
+  if (!device || *device == "cpu") return host;
+  return nestToDevice(host, *device);
+}
 
 void bind_envpool(py::module_& m) {
-  py::class_<EnvStepperFuture>(m, "EnvStepperFuture").def("result", &EnvStepperFuture::result);
+  py::class_<EnvStepperFuture>(m, "EnvStepperFuture").def("result", &EnvStepperFuture::result, py::arg("device") = py::none());
   py::class_<EnvStepper, std::shared_ptr<EnvStepper>>(m, "EnvPool",
                                                       "Batched Python environments in worker processes "
                                                       "(moolib.EnvPool API) writing into pinned, device-mapped slabs.")

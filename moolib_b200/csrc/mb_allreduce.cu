@@ -498,10 +498,8 @@ __device__ __forceinline__ void reduce_vecs(float* const* stage, uint32_t mask, 
   }
 }
 
-template <int NR>
-struct Unroll {
-  static constexpr int value = NR >= 8 ? 2 : NR >= 4 ? 4 : 8;  // U*NR = 16 loads of 16 B in flight per thread
-};
+// Default unroll: U*NR = 16 loads of 16 B in flight per thread.
+constexpr int default_unroll(int nr) { return nr >= 8 ? 2 : nr >= 4 ? 4 : 8; }
 
 __device__ __forceinline__ float4 scale_vec(const float4& a, float s, bool do_scale) {
   if (!do_scale) return a;
@@ -543,7 +541,7 @@ __device__ __forceinline__ Sink make_sink(const ArParams& p, uint8_t* smem) {
 
 // ---- K-A2 one-shot ----------------------------------------------------------------------------------------------
 
-template <int NR>
+template <int NR, int U>
 __global__ void __launch_bounds__(kArThreads, 1) ar_oneshot_kernel(const __grid_constant__ ArParams p) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ mb_ar_hdr s_total;
@@ -557,7 +555,6 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_oneshot_kernel(const __grid_
   // Each block-iteration owns a contiguous chunk of U*512 vectors (U*8 KiB): thread t handles chunk[k*512 + t],
   // k < U, all U*NR peer loads in flight before the first add.  (Lanes must never be clamped to a common address:
   // thousands of threads loading one peer line serialise on NVLink -- measured 10x slowdowns.)
-  constexpr int U = Unroll<NR>::value;
   constexpr uint64_t kChunk = (uint64_t)U * kArThreads;
   for (uint64_t base = (uint64_t)blockIdx.x * kChunk; base < p.total_vec; base += (uint64_t)gridDim.x * kChunk) {
     if (base + kChunk <= p.total_vec && !p.force_u1) {
@@ -583,7 +580,7 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_oneshot_kernel(const __grid_
 
 // ---- K-A2 two-shot ----------------------------------------------------------------------------------------------
 
-template <int NR>
+template <int NR, int U>
 __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_constant__ ArParams p) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
   __shared__ mb_ar_hdr s_total;
@@ -594,7 +591,6 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
   const mb_ar_hdr tot = s_total;
   const bool do_scale = p.scale && tot.num_gradients != 0;
   const float s = reduce_scale(p, tot);
-  constexpr int U = Unroll<NR>::value;
   constexpr uint64_t kChunk = (uint64_t)U * kArThreads;
   const uint64_t gstride = (uint64_t)gridDim.x * kChunk;
   // phase 1: reduce my slice and write it into every peer's staging (in place: slice `rank` of a peer's staging is
@@ -658,21 +654,33 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
 
 using ArKernel = void (*)(const ArParams);
 
-template <int NR>
+template <int NR, int U>
 ArKernel pick(bool twoshot) {
-  return twoshot ? (ArKernel)ar_twoshot_kernel<NR> : (ArKernel)ar_oneshot_kernel<NR>;
+  return twoshot ? (ArKernel)ar_twoshot_kernel<NR, U> : (ArKernel)ar_oneshot_kernel<NR, U>;
 }
 
-ArKernel kernel_for(int world, bool twoshot) {
+template <int NR>
+ArKernel pick_unroll(bool twoshot, int unroll) {
+  // U*NR <= 16 keeps the kernels under 128 registers at 512 threads
+  if (unroll >= 8 && NR <= 2) return pick<NR, 8>(twoshot);
+  if (unroll >= 4 && NR <= 4) return pick<NR, 4>(twoshot);
+  if (unroll >= 2) return pick<NR, 2>(twoshot);
+  return pick<NR, 1>(twoshot);
+}
+
+// Returns the kernel and the unroll it was instantiated with.
+ArKernel kernel_for(int world, bool twoshot, int want_unroll, int* unroll_out) {
+  int u = want_unroll >= 8 && world <= 2 ? 8 : want_unroll >= 4 && world <= 4 ? 4 : want_unroll >= 2 ? 2 : 1;
+  *unroll_out = u;
   switch (world) {
-    case 1: return pick<1>(twoshot);
-    case 2: return pick<2>(twoshot);
-    case 3: return pick<3>(twoshot);
-    case 4: return pick<4>(twoshot);
-    case 5: return pick<5>(twoshot);
-    case 6: return pick<6>(twoshot);
-    case 7: return pick<7>(twoshot);
-    case 8: return pick<8>(twoshot);
+    case 1: return pick_unroll<1>(twoshot, u);
+    case 2: return pick_unroll<2>(twoshot, u);
+    case 3: return pick_unroll<3>(twoshot, u);
+    case 4: return pick_unroll<4>(twoshot, u);
+    case 5: return pick_unroll<5>(twoshot, u);
+    case 6: return pick_unroll<6>(twoshot, u);
+    case 7: return pick_unroll<7>(twoshot, u);
+    case 8: return pick_unroll<8>(twoshot, u);
   }
   return nullptr;
 }
@@ -858,16 +866,25 @@ int launch_reduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* cons
   const int sms = sm_count(ctx->device);
   if (sms <= 0) return MB_ECUDA;
   const uint64_t work_vec = twoshot ? p.slice_vec : p.total_vec;
-  const uint64_t chunk = (uint64_t)kArThreads * (ctx->world >= 8 ? 2 : ctx->world >= 4 ? 4 : 8);  // Unroll<NR>
-  uint64_t want = (work_vec + chunk - 1) / chunk;
-  if (want == 0) want = 1;
   // One CTA per SM: with two, the per-block barrier pairs (block b <-> block b on every peer) run in two waves that start
   // at different times on different GPUs; measured on 2 B200: 8-64 MB rounds became bimodal (43 us vs 370 us).
   static const uint64_t blocks_per_sm = env_u64("MB_AR_BLOCKS_PER_SM", 1);
   static const uint64_t force_u1 = env_u64("MB_AR_FORCE_U1", 0);
+  static const uint64_t env_unroll = env_u64("MB_AR_UNROLL", 0);
+  const uint64_t max_grid = std::min<uint64_t>((uint64_t)sms * blocks_per_sm, kArMaxBlocks);
+  // Unroll: as many loads in flight per thread as fit (U*NR = 16), but never so coarse that SMs stay idle: a 4.4 MB
+  // gradient set at U=8 is only 67 chunks -- 67 of 148 SMs pulling over NVLink.
+  int want_unroll = env_unroll ? (int)env_unroll : default_unroll(ctx->world);
+  if (!env_unroll)
+    while (want_unroll > 1 && (work_vec + (uint64_t)kArThreads * want_unroll - 1) / ((uint64_t)kArThreads * want_unroll) < max_grid)
+      want_unroll >>= 1;
+  int unroll = 1;
+  ArKernel k = kernel_for(ctx->world, twoshot, want_unroll, &unroll);
+  const uint64_t chunk = (uint64_t)kArThreads * unroll;
+  uint64_t want = (work_vec + chunk - 1) / chunk;
+  if (want == 0) want = 1;
   p.force_u1 = (int32_t)force_u1;
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, std::min<uint64_t>((uint64_t)sms * blocks_per_sm, kArMaxBlocks));
-  ArKernel k = kernel_for(ctx->world, twoshot);
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, max_grid);
   const size_t smem = table_bytes(ntab);
   int rc = ensure_dyn_smem(reinterpret_cast<const void*>(k), smem);
   if (rc) return rc;

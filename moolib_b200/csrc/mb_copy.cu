@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
+#include <vector>
 
 namespace mb {
 namespace {
@@ -45,6 +47,21 @@ struct CopyParams {
   uint8_t tma_stores;  // store groups allowed to be still reading shared memory
 };
 static_assert(sizeof(CopyParams) <= 4000, "CopyParams must fit the 4 KiB kernel parameter block");
+
+// The same table in DEVICE memory (mb_copy2d_table): any number of jobs in one launch.  Uploaded once per launch by
+// one async copy from the context's pinned staging; the kernels read it through L1/L2.
+struct CopyParamsG {
+  const mb_copy_job* jobs;
+  const uint32_t* tile_start;  // njobs + 1
+  const uint32_t* aux;
+  const uint8_t* mode;
+  uint32_t njobs;
+  uint32_t n_tma;
+  uint32_t tma_tile;
+  uint16_t tma_warps;
+  uint8_t tma_stages;
+  uint8_t tma_stores;
+};
 
 // ---- span copies -------------------------------------------------------------------------------------------------
 
@@ -202,8 +219,9 @@ __device__ __forceinline__ void run_tile(const mb_copy_job& j, uint32_t mode, ui
   }
 }
 
-__device__ __forceinline__ uint32_t find_job(const CopyParams& p, uint32_t t) {
-  // binary search: last job whose tile_start <= t (njobs <= 64 -> <= 6 steps, warp-uniform)
+template <class P>
+__device__ __forceinline__ uint32_t find_job(const P& p, uint32_t t) {
+  // binary search: last job whose tile_start <= t (warp-uniform; <= 6 steps for an inline table)
   uint32_t lo = 0, hi = p.njobs;
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
@@ -212,13 +230,17 @@ __device__ __forceinline__ uint32_t find_job(const CopyParams& p, uint32_t t) {
   return lo;
 }
 
-__global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_kernel(const __grid_constant__ CopyParams p) {
+template <class P>
+__device__ __forceinline__ void ldg_body(const P& p) {
   const uint32_t total = p.tile_start[p.njobs];
   for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
     const uint32_t j = find_job(p, t);
-    run_tile(p.jobs[j], p.mode[j], p.aux[j], t - p.tile_start[j], threadIdx.x, kCopyThreads);
+    const mb_copy_job job = p.jobs[j];
+    run_tile(job, p.mode[j], p.aux[j], t - p.tile_start[j], threadIdx.x, kCopyThreads);
   }
 }
+__global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_kernel(const __grid_constant__ CopyParams p) { ldg_body(p); }
+__global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_table_kernel(const CopyParamsG p) { ldg_body(p); }
 
 // Pointer-array gather (uniform rows, DEVICE-resident row pointers): K-B1 / K-B4.
 struct GatherParams {
@@ -313,13 +335,14 @@ struct TmaTile {
 };
 
 // For the bulk class, tile_start / aux are in units of p.tma_tile (aux = tiles per row; rows are tiled one by one).
-__device__ __forceinline__ TmaTile tma_decode(const CopyParams& p, uint32_t t) {
+template <class P>
+__device__ __forceinline__ TmaTile tma_decode(const P& p, uint32_t t) {
   uint32_t lo = 0, hi = p.n_tma;
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
     if (p.tile_start[mid] <= t) lo = mid; else hi = mid;
   }
-  const mb_copy_job& j = p.jobs[lo];
+  const mb_copy_job j = p.jobs[lo];
   const uint32_t lt = t - p.tile_start[lo];
   const uint32_t tpr = p.aux[lo];
   const uint32_t row = lt / tpr;
@@ -331,7 +354,8 @@ __device__ __forceinline__ TmaTile tma_decode(const CopyParams& p, uint32_t t) {
   return r;
 }
 
-__global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_kernel(const __grid_constant__ CopyParams p) {
+template <class P>
+__device__ __forceinline__ void hybrid_body(const P& p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[kHybridWarps][kMaxTmaStages];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -343,7 +367,8 @@ __global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_kernel(con
     const uint32_t tid = threadIdx.x - p.tma_warps * 32;
     for (uint32_t t = tma_total + blockIdx.x; t < total; t += gridDim.x) {
       const uint32_t j = find_job(p, t);
-      run_tile(p.jobs[j], p.mode[j], p.aux[j], t - p.tile_start[j], tid, nthr);
+      const mb_copy_job job = p.jobs[j];
+      run_tile(job, p.mode[j], p.aux[j], t - p.tile_start[j], tid, nthr);
     }
     return;
   }
@@ -388,6 +413,10 @@ __global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_kernel(con
   }
   bulk_wait_all();
 }
+__global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_kernel(const __grid_constant__ CopyParams p) {
+  hybrid_body(p);
+}
+__global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_table_kernel(const CopyParamsG p) { hybrid_body(p); }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 
@@ -408,6 +437,7 @@ struct CopyTuning {
   uint32_t tma_stores;    // store groups in flight per warp
   uint32_t tma_warps;     // ring-driving warps per CTA (the other 8 - tma_warps warps run the LDG path)
   uint64_t tma_min_bytes; // auto: use the hybrid kernel when the bulk class carries at least this much
+  int host_src_ctas;      // LDG grid cap when a table reads host-mapped memory (PCIe-bound)
 };
 
 const CopyTuning& tuning() {
@@ -423,6 +453,7 @@ const CopyTuning& tuning() {
     c.tma_stores = (uint32_t)env_long("MB_TMA_STORES", c.tma_stages / 2, 1, 7);
     if (c.tma_stores >= c.tma_stages) c.tma_stores = c.tma_stages - 1;
     c.tma_min_bytes = (uint64_t)env_long("MB_TMA_MIN_BYTES", 1l << 20, 0, 1l << 40);
+    c.host_src_ctas = (int)env_long("MB_COPY_HOST_SRC_CTAS", 64, 1, 4096);
     return c;
   }();
   return t;
@@ -444,17 +475,38 @@ int validate_job(const mb_copy_job& j, int i) {
 }
 
 std::mutex g_attr_mu;
-uint32_t g_hybrid_smem_set = 0;
+uint32_t g_hybrid_smem_set[2] = {0, 0};  // [inline kernel, table kernel]
 
-int launch_chunk(const mb_copy_job* jobs, int n, cudaStream_t stream) {
+// Where the caller says the sources live (MB_SRC_*); UNKNOWN asks the driver per job.
+bool source_is_device(const mb_copy_job& j, int src_kind) {
+  if (src_kind == MB_SRC_DEVICE) return true;
+  if (src_kind == MB_SRC_HOST_MAPPED) return false;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, j.src) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice;
+}
+
+// What a launch needs besides the table itself.
+struct TablePlan {
+  uint32_t njobs = 0, n_tma = 0;
+  uint64_t tiles = 0, tma_tiles = 0;
+  bool hybrid = false;
+  bool any_host_src = false;
+};
+
+// Normalise `n` jobs, order the bulk-async class first and fill the table arrays (capacity >= n, tile_start n + 1).
+// Shared by the inline (kernel-parameter) and the device-table launches.
+int build_table(const mb_copy_job* jobs, int n, int src_kind, mb_copy_job* out_jobs, uint32_t* tile_start, uint32_t* aux,
+                uint8_t* mode, std::vector<uint8_t>& bulk_scratch, TablePlan* plan) {
   const CopyTuning& tn = tuning();
-  CopyParams p;
-  std::memset(&p, 0, sizeof(p));
-  // normalise, then order the bulk-async class first
-  mb_copy_job norm[kMaxJobs];
-  bool bulk[kMaxJobs];
+  bulk_scratch.resize((size_t)n);
+  uint8_t* bulk = bulk_scratch.data();
   uint32_t nj = 0;
   uint64_t bulk_bytes = 0;
+  // pass 1: normalise into the tail of out_jobs' capacity order (stable), remember the class
   for (int i = 0; i < n; ++i) {
     if (jobs[i].rows == 0 || jobs[i].row_bytes == 0) continue;
     mb_copy_job j = jobs[i];
@@ -462,86 +514,122 @@ int launch_chunk(const mb_copy_job* jobs, int n, cudaStream_t stream) {
       j.row_bytes *= j.rows;  // contiguous on both sides: one long row
       j.rows = 1;
     }
-    bulk[nj] = tn.impl != kImplLdg && job_tma_ok(j);
-    if (bulk[nj]) {
-      // Host-mapped sources (pinned EnvPool slabs) stay on the LDG path, which is the one validated for zero-copy
-      // reads over PCIe; the bulk-async path is for device-resident sources.
-      cudaPointerAttributes attr;
-      if (cudaPointerGetAttributes(&attr, j.src) != cudaSuccess) {
-        cudaGetLastError();
-        bulk[nj] = false;
-      } else if (attr.type != cudaMemoryTypeDevice) {
-        bulk[nj] = false;
-      }
+    bool is_bulk = tn.impl != kImplLdg && job_tma_ok(j);
+    // Host-mapped sources (pinned EnvPool slabs) stay on the LDG path, which is the one validated for zero-copy
+    // reads over PCIe; the bulk-async path is for device-resident sources.
+    const bool dev_src = (is_bulk || src_kind != MB_SRC_UNKNOWN) ? source_is_device(j, src_kind) : true;
+    if (!dev_src) {
+      is_bulk = false;
+      plan->any_host_src = true;
     }
-    if (bulk[nj]) bulk_bytes += j.rows * j.row_bytes;
-    norm[nj++] = j;
+    bulk[nj] = is_bulk;
+    if (is_bulk) bulk_bytes += j.rows * j.row_bytes;
+    out_jobs[nj++] = j;
   }
-  if (nj == 0) return 0;
-  const bool hybrid = bulk_bytes > 0 && (tn.impl == kImplTma || bulk_bytes >= tn.tma_min_bytes);
-  uint32_t k = 0;
-  if (hybrid) {
-    for (uint32_t i = 0; i < nj; ++i)
-      if (bulk[i]) { p.jobs[k] = norm[i]; p.mode[k++] = kModeTma; }
-    p.n_tma = k;
-    for (uint32_t i = 0; i < nj; ++i)
-      if (!bulk[i]) p.jobs[k++] = norm[i];
-  } else {
-    for (uint32_t i = 0; i < nj; ++i) p.jobs[k++] = norm[i];
+  plan->njobs = nj;
+  if (nj == 0) return MB_OK;
+  plan->hybrid = bulk_bytes > 0 && (tn.impl == kImplTma || bulk_bytes >= tn.tma_min_bytes);
+  if (plan->hybrid) {
+    // stable partition: the bulk-async class first, the rest behind it in their original order
+    static thread_local std::vector<mb_copy_job> rest;
+    rest.clear();
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < nj; ++i) {
+      if (bulk[i]) out_jobs[k++] = out_jobs[i];  // k <= i: never overwrites an unread entry
+      else rest.push_back(out_jobs[i]);
+    }
+    plan->n_tma = k;
+    for (const mb_copy_job& j : rest) out_jobs[k++] = j;
   }
-  p.njobs = nj;
-  p.tma_tile = tn.tma_tile;
-  p.tma_warps = (uint16_t)tn.tma_warps;
-  p.tma_stages = (uint8_t)tn.tma_stages;
-  p.tma_stores = (uint8_t)tn.tma_stores;
   uint64_t tiles = 0;
   for (uint32_t i = 0; i < nj; ++i) {
-    const mb_copy_job& j = p.jobs[i];
-    p.tile_start[i] = (uint32_t)tiles;
+    const mb_copy_job& j = out_jobs[i];
+    tile_start[i] = (uint32_t)tiles;
     uint64_t t;
-    if (i < p.n_tma) {
+    if (i < plan->n_tma) {
       const uint64_t tpr = (j.row_bytes + tn.tma_tile - 1) / tn.tma_tile;
-      p.aux[i] = (uint32_t)tpr;
+      mode[i] = kModeTma;
+      aux[i] = (uint32_t)tpr;
       t = tpr * j.rows;
     } else if (j.row_bytes >= kTileBytes) {
       const uint64_t tpr = (j.row_bytes + kTileBytes - 1) / kTileBytes;
-      p.mode[i] = kModeBigRows;
-      p.aux[i] = (uint32_t)tpr;
+      mode[i] = kModeBigRows;
+      aux[i] = (uint32_t)tpr;
       t = tpr * j.rows;
     } else {
       const uint64_t rpt = std::max<uint64_t>(1, kTileBytes / j.row_bytes);
       const bool v16 = aligned16(reinterpret_cast<uintptr_t>(j.src)) && aligned16(reinterpret_cast<uintptr_t>(j.dst)) &&
                        aligned16(j.row_bytes) && aligned16((uint64_t)j.src_pitch) && aligned16((uint64_t)j.dst_pitch);
-      p.mode[i] = v16 ? kModeSmallVec16 : kModeSmallGeneric;
-      p.aux[i] = (uint32_t)rpt;
+      mode[i] = v16 ? kModeSmallVec16 : kModeSmallGeneric;
+      aux[i] = (uint32_t)rpt;
       t = (j.rows + rpt - 1) / rpt;
     }
     tiles += t;
+    if (i + 1 == plan->n_tma) plan->tma_tiles = tiles;
     if (tiles >= (1ull << 31)) {
-      set_error("mb_copy2d_batch: too many tiles in one launch");
+      set_error("mb_copy2d: too many tiles in one launch");
       return MB_EINVAL;
     }
   }
-  p.tile_start[nj] = (uint32_t)tiles;
+  tile_start[nj] = (uint32_t)tiles;
+  plan->tiles = tiles;
+  return MB_OK;
+}
+
+struct LaunchShape {
+  uint32_t grid = 0, smem = 0;
+};
+
+int launch_shape(const TablePlan& plan, int which_kernel, LaunchShape* out) {
+  const CopyTuning& tn = tuning();
   const int sms = sm_count(current_device());
   if (sms <= 0) return MB_ECUDA;
-  if (hybrid) {
+  if (plan.hybrid) {
     const uint32_t smem = tn.tma_warps * tn.tma_stages * tn.tma_tile;
     {
       std::lock_guard<std::mutex> l(g_attr_mu);
-      if (g_hybrid_smem_set < smem) {
-        MB_CUDA(cudaFuncSetAttribute(copy2d_hybrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        g_hybrid_smem_set = smem;
+      if (g_hybrid_smem_set[which_kernel] < smem) {
+        if (which_kernel == 0)
+          MB_CUDA(cudaFuncSetAttribute(copy2d_hybrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+          MB_CUDA(cudaFuncSetAttribute(copy2d_hybrid_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g_hybrid_smem_set[which_kernel] = smem;
       }
     }
-    const uint64_t tma_tiles = p.tile_start[p.n_tma];
-    const uint64_t want = std::max<uint64_t>((tma_tiles + tn.tma_warps - 1) / tn.tma_warps, tiles - tma_tiles);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms);
-    copy2d_hybrid_kernel<<<grid, kHybridWarps * 32, smem, stream>>>(p);
+    const uint64_t want = std::max<uint64_t>((plan.tma_tiles + tn.tma_warps - 1) / tn.tma_warps, plan.tiles - plan.tma_tiles);
+    out->grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms);
+    out->smem = smem;
   } else {
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)sms * tn.ctas_per_sm);
-    copy2d_ldg_kernel<<<grid, kCopyThreads, 0, stream>>>(p);
+    uint64_t cap = (uint64_t)sms * tn.ctas_per_sm;
+    // sources in host-mapped memory are PCIe-bound: a few dozen CTAs keep the link full, the SMs stay free for the
+    // kernels of other streams (actor inference) instead of hosting warps that wait on PCIe round trips
+    if (plan.any_host_src) cap = std::min<uint64_t>(cap, (uint64_t)tn.host_src_ctas);
+    out->grid = (uint32_t)std::min<uint64_t>(plan.tiles, cap);
+    out->smem = 0;
   }
+  return MB_OK;
+}
+
+int launch_chunk(const mb_copy_job* jobs, int n, int src_kind, cudaStream_t stream) {
+  const CopyTuning& tn = tuning();
+  CopyParams p;
+  std::memset(&p, 0, sizeof(p));
+  static thread_local std::vector<uint8_t> scratch;
+  TablePlan plan;
+  int rc = build_table(jobs, n, src_kind, p.jobs, p.tile_start, p.aux, p.mode, scratch, &plan);
+  if (rc) return rc;
+  if (plan.njobs == 0) return 0;
+  p.njobs = plan.njobs;
+  p.n_tma = plan.n_tma;
+  p.tma_tile = tn.tma_tile;
+  p.tma_warps = (uint16_t)tn.tma_warps;
+  p.tma_stages = (uint8_t)tn.tma_stages;
+  p.tma_stores = (uint8_t)tn.tma_stores;
+  LaunchShape ls;
+  rc = launch_shape(plan, 0, &ls);
+  if (rc) return rc;
+  if (plan.hybrid) copy2d_hybrid_kernel<<<ls.grid, kHybridWarps * 32, ls.smem, stream>>>(p);
+  else copy2d_ldg_kernel<<<ls.grid, kCopyThreads, 0, stream>>>(p);
   MB_CUDA(cudaGetLastError());
   return 1;
 }
@@ -549,12 +637,30 @@ int launch_chunk(const mb_copy_job* jobs, int n, cudaStream_t stream) {
 }  // namespace
 }  // namespace mb
 
+// A context owns the staging for device-resident job tables: `depth` slots of pinned host memory + device memory.
+struct mb_copy_ctx {
+  int device = 0;
+  uint32_t max_jobs = 0;
+  static constexpr int kDepth = 4;
+  struct Slot {
+    uint8_t* host = nullptr;
+    uint8_t* dev = nullptr;
+    cudaEvent_t done = nullptr;
+    bool used = false;
+  } slot[kDepth];
+  size_t off_tile = 0, off_aux = 0, off_mode = 0, bytes = 0;
+  int next = 0;
+  std::mutex mu;
+  std::vector<uint8_t> scratch;
+};
+
 using namespace mb;
 
 extern "C" {
 
-int mb_copy2d_batch(const mb_copy_job* jobs, int njobs, mb_stream_t stream_) {
+int mb_copy2d_batch_ex(const mb_copy_job* jobs, int njobs, int src_kind, mb_stream_t stream_) {
   MB_CHECK_ARG(njobs >= 0 && (jobs != nullptr || njobs == 0), "mb_copy2d_batch: bad job table");
+  MB_CHECK_ARG(src_kind >= MB_SRC_UNKNOWN && src_kind <= MB_SRC_HOST_MAPPED, "mb_copy2d_batch: bad src_kind %d", src_kind);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   for (int i = 0; i < njobs; ++i) {
     int rc = validate_job(jobs[i], i);
@@ -562,9 +668,112 @@ int mb_copy2d_batch(const mb_copy_job* jobs, int njobs, mb_stream_t stream_) {
   }
   int launches = 0;
   for (int i = 0; i < njobs; i += kMaxJobs) {
-    int rc = launch_chunk(jobs + i, std::min(kMaxJobs, njobs - i), stream);
+    int rc = launch_chunk(jobs + i, std::min(kMaxJobs, njobs - i), src_kind, stream);
     if (rc < 0) return rc;
     launches += rc;
+  }
+  return launches;
+}
+
+int mb_copy2d_batch(const mb_copy_job* jobs, int njobs, mb_stream_t stream) {
+  return mb_copy2d_batch_ex(jobs, njobs, MB_SRC_UNKNOWN, stream);
+}
+
+int mb_copy_ctx_create(int device, uint32_t max_jobs, mb_copy_ctx** out) {
+  MB_CHECK_ARG(out != nullptr, "mb_copy_ctx_create: out is null");
+  *out = nullptr;
+  MB_CHECK_ARG(max_jobs >= 1 && max_jobs <= (1u << 20), "mb_copy_ctx_create: max_jobs %u not in [1, 2^20]", max_jobs);
+  int prev = -1;
+  MB_CUDA(cudaGetDevice(&prev));
+  MB_CUDA(cudaSetDevice(device));
+  mb_copy_ctx* c = new (std::nothrow) mb_copy_ctx();
+  if (!c) return MB_ENOMEM;
+  c->device = device;
+  c->max_jobs = max_jobs;
+  auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+  c->off_tile = up((size_t)max_jobs * sizeof(mb_copy_job));
+  c->off_aux = c->off_tile + up(((size_t)max_jobs + 1) * 4);
+  c->off_mode = c->off_aux + up((size_t)max_jobs * 4);
+  c->bytes = c->off_mode + up((size_t)max_jobs);
+  int rc = MB_OK;
+  for (auto& sl : c->slot) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&sl.host), c->bytes, cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&sl.dev), c->bytes) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess) {
+      rc = cuda_fail(cudaGetLastError(), "mb_copy_ctx_create allocation", __FILE__, __LINE__);
+      break;
+    }
+  }
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
+  if (rc != MB_OK) {
+    mb_copy_ctx_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return MB_OK;
+}
+
+int mb_copy_ctx_destroy(mb_copy_ctx* c) {
+  if (!c) return MB_OK;
+  for (auto& sl : c->slot) {
+    if (sl.done) {
+      if (sl.used) cudaEventSynchronize(sl.done);
+      cudaEventDestroy(sl.done);
+    }
+    if (sl.host) cudaFreeHost(sl.host);
+    if (sl.dev) cudaFree(sl.dev);
+  }
+  delete c;
+  return MB_OK;
+}
+
+int mb_copy2d_table(mb_copy_ctx* c, const mb_copy_job* jobs, int njobs, int src_kind, mb_stream_t stream_) {
+  MB_CHECK_ARG(c != nullptr, "mb_copy2d_table: null context");
+  MB_CHECK_ARG(njobs >= 0 && (jobs != nullptr || njobs == 0), "mb_copy2d_table: bad job table");
+  MB_CHECK_ARG(src_kind >= MB_SRC_UNKNOWN && src_kind <= MB_SRC_HOST_MAPPED, "mb_copy2d_table: bad src_kind %d", src_kind);
+  if (njobs <= kMaxJobs) return mb_copy2d_batch_ex(jobs, njobs, src_kind, stream_);  // fits the kernel parameters
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  for (int i = 0; i < njobs; ++i) {
+    int rc = validate_job(jobs[i], i);
+    if (rc) return rc;
+  }
+  const CopyTuning& tn = tuning();
+  std::lock_guard<std::mutex> l(c->mu);
+  int launches = 0;
+  for (int first = 0; first < njobs; first += (int)c->max_jobs) {
+    const int n = std::min<int>((int)c->max_jobs, njobs - first);
+    mb_copy_ctx::Slot& sl = c->slot[c->next];
+    c->next = (c->next + 1) % mb_copy_ctx::kDepth;
+    if (sl.used) MB_CUDA(cudaEventSynchronize(sl.done));  // the upload that last used this pinned slot has finished
+    TablePlan plan;
+    int rc = build_table(jobs + first, n, src_kind, reinterpret_cast<mb_copy_job*>(sl.host),
+                         reinterpret_cast<uint32_t*>(sl.host + c->off_tile), reinterpret_cast<uint32_t*>(sl.host + c->off_aux),
+                         sl.host + c->off_mode, c->scratch, &plan);
+    if (rc) return rc;
+    if (plan.njobs == 0) continue;
+    // one upload: [jobs | tile_start | aux | mode] up to the last byte in use
+    const size_t upload = c->off_mode + plan.njobs;
+    MB_CUDA(cudaMemcpyAsync(sl.dev, sl.host, upload, cudaMemcpyHostToDevice, stream));
+    CopyParamsG p;
+    p.jobs = reinterpret_cast<const mb_copy_job*>(sl.dev);
+    p.tile_start = reinterpret_cast<const uint32_t*>(sl.dev + c->off_tile);
+    p.aux = reinterpret_cast<const uint32_t*>(sl.dev + c->off_aux);
+    p.mode = sl.dev + c->off_mode;
+    p.njobs = plan.njobs;
+    p.n_tma = plan.n_tma;
+    p.tma_tile = tn.tma_tile;
+    p.tma_warps = (uint16_t)tn.tma_warps;
+    p.tma_stages = (uint8_t)tn.tma_stages;
+    p.tma_stores = (uint8_t)tn.tma_stores;
+    LaunchShape ls;
+    rc = launch_shape(plan, 1, &ls);
+    if (rc) return rc;
+    if (plan.hybrid) copy2d_hybrid_table_kernel<<<ls.grid, kHybridWarps * 32, ls.smem, stream>>>(p);
+    else copy2d_ldg_table_kernel<<<ls.grid, kCopyThreads, 0, stream>>>(p);
+    MB_CUDA(cudaGetLastError());
+    MB_CUDA(cudaEventRecord(sl.done, stream));
+    sl.used = true;
+    ++launches;
   }
   return launches;
 }

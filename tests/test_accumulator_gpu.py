@@ -131,7 +131,8 @@ def test_parallel_gradients_on_gpu():
             acc.reduce_gradients(10)
             fed += 1
     tm = acc.reduce_timings()
-    assert tm["zero_copy_rounds"] == 6 and tm["stage_launches"] == 0
+    # the very first contribution found an ordinary .grad tensor (created before the NVLink context existed): K-A1
+    assert tm["zero_copy_rounds"] == 5 and tm["stage_launches"] == 1
 
 
 WORKER = r"""

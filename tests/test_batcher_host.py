@@ -138,3 +138,80 @@ def test_stack_and_unstack_fields_roundtrip():
     assert one["o"].shape == (1, 3, 2) and one["t"][1] == ("s0",)
     back = _C.unstack_fields(one, 1, 0)[0]
     assert back["o"].equal(items[0]["o"]) and back["t"][1] == "s0"
+
+
+def _unroll_reference(items, extras, T, Bl, device="cpu"):
+    """Batcher(T).stack x T followed by Batcher(Bl, dim=1).cat -- the two-pass composition UnrollBatcher fuses."""
+    tb, lb = moolib_b200.Batcher(T, device), moolib_b200.Batcher(Bl, device, dim=1)
+    outs, k = [], 0
+    for it in items:
+        tb.stack(it)
+        if not tb.empty():
+            data = tb.get()
+            if extras is not None:
+                data["extra"] = extras[k]
+            k += 1
+            lb.cat(data)
+            while not lb.empty():
+                outs.append(lb.get())
+    return outs
+
+
+def _same_nest(a, b):
+    if isinstance(a, dict):
+        return isinstance(b, dict) and list(a) == list(b) and all(_same_nest(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)):
+        return type(a) is type(b) and len(a) == len(b) and all(_same_nest(x, y) for x, y in zip(a, b))
+    if isinstance(a, torch.Tensor):
+        return a.dtype == b.dtype and a.shape == b.shape and a.equal(b)
+    return a == b
+
+
+@pytest.mark.parametrize("B,Bl", [(8, 4), (6, 4), (5, 7), (4, 4), (3, 1)])
+def test_unroll_batcher_equals_stack_then_cat(B, Bl):
+    """Host logic of UnrollBatcher on CPU tensors (carry across unrolls when B is not a multiple of the learner batch,
+    nested items, pass-through leaves, the extra nest that is concatenated only)."""
+    T, U = 5, 4
+    g = torch.Generator().manual_seed(B * 100 + Bl)
+    items, extras = [], []
+    for u in range(U):
+        for t in range(T):
+            items.append({"obs": {"state": torch.randint(0, 255, (B, 2, 3), dtype=torch.uint8, generator=g),
+                                  "reward": torch.randn(B, generator=g)},
+                          "act": [torch.randint(0, 9, (B,), generator=g), (torch.randn(B, 4, generator=g),)],
+                          "tag": f"u{u}t{t}"})
+        extras.append((torch.randn(2, B, 3, generator=g), torch.randn(1, B, generator=g)))
+    ub = moolib_b200.UnrollBatcher(T, Bl, "cpu", cat_dim=1)
+    got = []
+    for i, it in enumerate(items):
+        if i % T == T - 1:
+            ub.set_extra("extra", extras[i // T])
+        ub.stack(it)
+        while not ub.empty():
+            got.append(ub.get())
+    exp = _unroll_reference(items, extras, T, Bl)
+    assert len(got) == len(exp) == (U * B) // Bl
+    for a, b in zip(got, exp):
+        assert _same_nest(a, b)
+        assert a["obs"]["state"].shape == (T, Bl, 2, 3) and a["extra"][0].shape == (2, Bl, 3)
+
+
+def test_unroll_batcher_errors():
+    with pytest.raises(RuntimeError, match="cat_dim must be >= 1"):
+        moolib_b200.UnrollBatcher(3, 2, "cpu", cat_dim=0)
+    ub = moolib_b200.UnrollBatcher(3, 2, "cpu")
+    ub.stack({"a": torch.zeros(4, 2)})
+    with pytest.raises(RuntimeError, match="same shapes and dtypes"):
+        ub.stack({"a": torch.zeros(4, 3)})
+    with pytest.raises(RuntimeError, match="type mismatch in batch operation"):
+        ub.stack({"a": 3})
+    ub = moolib_b200.UnrollBatcher(2, 2, "cpu")
+    ub.stack({"a": torch.zeros(4), "b": torch.zeros(3)})
+    with pytest.raises(RuntimeError, match="all tensors must have the same size in the batch dimension"):
+        ub.stack({"a": torch.zeros(4), "b": torch.zeros(3)})
+
+
+def test_to_device_cpu_is_identity_nest():
+    nest = {"a": torch.arange(4), "b": (torch.ones(2), "s")}
+    out = moolib_b200.to_device(nest, "cpu")
+    assert _same_nest(out, nest) and out["b"][1] == "s"

@@ -25,7 +25,15 @@ before = _C.kernel_launches()
 stacked = []
 for t in range(steps):
     action = torch.from_numpy(rng.integers(0, 18, size=bs, dtype=np.int64)).cuda()   # CUDA action tensor
-    obs = envs.step(t % 2, action).result()
+    fut = envs.step(t % 2, action)
+    obs = fut.result()
+    if t >= 2 and t % 3 == 0:
+        # EnvStepperFuture.result(device=...): every key on the device, read from the pinned slab by ONE launch
+        l0 = _C.kernel_launches()
+        dev_obs = fut.result(device='cuda:0')
+        assert _C.kernel_launches() - l0 == 1
+        for k in ('state', 'reward', 'done'):
+            assert dev_obs[k].device.type == 'cuda' and dev_obs[k].cpu().numpy().tobytes() == g[f'{k}{t}'].tobytes(), (k, t)
     assert obs['state'].numpy().tobytes() == g[f'state{t}'].tobytes(), t
     assert obs['reward'].numpy().tobytes() == g[f'reward{t}'].tobytes(), t
     assert obs['done'].numpy().tobytes() == g[f'done{t}'].tobytes(), t
