@@ -167,10 +167,10 @@ def test_copy_table_through_the_c_abi_matches_oracle():
     from moolib_b200 import _lib
 
     rng = np.random.Generator(np.random.PCG64(77))
-    src = rng.integers(0, 256, size=48 << 20, dtype=np.uint8)
-    dst_exp = np.zeros(48 << 20, dtype=np.uint8)
+    src = rng.integers(0, 256, size=128 << 20, dtype=np.uint8)
+    dst_exp = np.zeros(128 << 20, dtype=np.uint8)
     s_dev = torch.from_numpy(src).to(DEV)
-    d_dev = torch.zeros(48 << 20, dtype=torch.uint8, device=DEV)
+    d_dev = torch.zeros(128 << 20, dtype=torch.uint8, device=DEV)
     jobs, dpos, spos = [], 0, 0
     for i in range(1500):
         kind = i % 5
