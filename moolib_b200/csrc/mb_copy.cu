@@ -45,6 +45,7 @@ struct CopyParams {
   uint16_t tma_warps;  // warps driving rings
   uint8_t tma_stages;
   uint8_t tma_stores;  // store groups allowed to be still reading shared memory
+  uint8_t tma_contig;  // tile assignment of the ring workers: 0 strided, 1 contiguous spans
 };
 static_assert(sizeof(CopyParams) <= 4000, "CopyParams must fit the 4 KiB kernel parameter block");
 
@@ -61,6 +62,7 @@ struct CopyParamsG {
   uint16_t tma_warps;
   uint8_t tma_stages;
   uint8_t tma_stores;
+  uint8_t tma_contig;
 };
 
 // ---- span copies -------------------------------------------------------------------------------------------------
@@ -237,26 +239,35 @@ __device__ __forceinline__ uint32_t seek_job(const P& p, uint32_t t, uint32_t cu
   return lo;
 }
 
+// Tiles [lo, hi) of the LDG class, executed by `nthr` threads of CTA blockIdx.x.  Strided assignment for inline tables
+// (few jobs, parameter space); contiguous spans for device-resident tables, so that a CTA's consecutive tiles are
+// consecutive jobs and the table cursor moves one entry at a time (a unroll gather has ~1000 one-tile jobs: with a
+// strided assignment every tile paid a ~20-load search, which made the tiny leaves the critical path).
 template <class P>
-__device__ __forceinline__ uint32_t find_job(const P& p, uint32_t t) {
-  // binary search: last job whose tile_start <= t (warp-uniform; <= 6 steps for an inline table)
-  uint32_t lo = 0, hi = p.njobs;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (p.tile_start[mid] <= t) lo = mid; else hi = mid;
+__device__ __forceinline__ void ldg_tiles(const P& p, uint32_t lo, uint32_t hi, uint32_t first_job, uint32_t tid,
+                                          uint32_t nthr) {
+  uint32_t t, step, end;
+  if (p.tma_contig) {
+    const uint32_t per = (hi - lo + gridDim.x - 1) / gridDim.x;
+    t = lo + blockIdx.x * per;
+    end = min(hi, t + per);
+    step = 1;
+  } else {
+    t = lo + blockIdx.x;
+    end = hi;
+    step = gridDim.x;
   }
-  return lo;
+  uint32_t j = first_job;
+  for (; t < end; t += step) {
+    j = seek_job(p, t, j, p.njobs);
+    const mb_copy_job job = p.jobs[j];
+    run_tile(job, p.mode[j], p.aux[j], t - p.tile_start[j], tid, nthr);
+  }
 }
 
 template <class P>
 __device__ __forceinline__ void ldg_body(const P& p) {
-  const uint32_t total = p.tile_start[p.njobs];
-  uint32_t j = 0;
-  for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
-    j = seek_job(p, t, j, p.njobs);
-    const mb_copy_job job = p.jobs[j];
-    run_tile(job, p.mode[j], p.aux[j], t - p.tile_start[j], threadIdx.x, kCopyThreads);
-  }
+  ldg_tiles(p, 0, p.tile_start[p.njobs], 0, threadIdx.x, kCopyThreads);
 }
 __global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_kernel(const __grid_constant__ CopyParams p) { ldg_body(p); }
 __global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_table_kernel(const CopyParamsG p) { ldg_body(p); }
@@ -354,18 +365,38 @@ struct TmaTile {
 };
 
 // For the bulk class, tile_start / aux are in units of p.tma_tile (aux = tiles per row; rows are tiled one by one).
+// A stream of tiles (the load stream or the store stream of one ring) keeps the job it is in: the table is consulted
+// again only when a tile leaves that job's range.
+struct TmaCursor {
+  uint32_t job = 0, t0 = 1, t1 = 0;  // cached job and its tile range [t0, t1); empty at start
+  uint32_t tpr = 1;
+  const uint8_t* src = nullptr;
+  uint8_t* dst = nullptr;
+  uint64_t row_bytes = 0;
+  int64_t src_pitch = 0, dst_pitch = 0;
+};
+
 template <class P>
-__device__ __forceinline__ TmaTile tma_decode(const P& p, uint32_t t, uint32_t& cursor) {
-  const uint32_t lo = cursor = seek_job(p, t, cursor, p.n_tma);
-  const mb_copy_job j = p.jobs[lo];
-  const uint32_t lt = t - p.tile_start[lo];
-  const uint32_t tpr = p.aux[lo];
-  const uint32_t row = lt / tpr;
-  const uint64_t col = (uint64_t)(lt - row * tpr) * p.tma_tile;
+__device__ __forceinline__ TmaTile tma_decode(const P& p, uint32_t t, TmaCursor& c) {
+  if (t < c.t0 || t >= c.t1) {
+    c.job = seek_job(p, t, t >= c.t1 && c.t1 != 0 ? c.job : 0u, p.n_tma);
+    const mb_copy_job j = p.jobs[c.job];
+    c.t0 = p.tile_start[c.job];
+    c.t1 = p.tile_start[c.job + 1];
+    c.tpr = p.aux[c.job];
+    c.src = static_cast<const uint8_t*>(j.src);
+    c.dst = static_cast<uint8_t*>(j.dst);
+    c.row_bytes = j.row_bytes;
+    c.src_pitch = j.src_pitch;
+    c.dst_pitch = j.dst_pitch;
+  }
+  const uint32_t lt = t - c.t0;
+  const uint32_t row = lt / c.tpr;
+  const uint64_t col = (uint64_t)(lt - row * c.tpr) * p.tma_tile;
   TmaTile r;
-  r.src = static_cast<const uint8_t*>(j.src) + (int64_t)row * j.src_pitch + col;
-  r.dst = static_cast<uint8_t*>(j.dst) + (int64_t)row * j.dst_pitch + col;
-  r.bytes = (uint32_t)min((uint64_t)p.tma_tile, j.row_bytes - col);
+  r.src = c.src + (int64_t)row * c.src_pitch + col;
+  r.dst = c.dst + (int64_t)row * c.dst_pitch + col;
+  r.bytes = (uint32_t)min((uint64_t)p.tma_tile, c.row_bytes - col);
   return r;
 }
 
@@ -377,15 +408,8 @@ __device__ __forceinline__ void hybrid_body(const P& p) {
   const uint32_t tma_total = p.tile_start[p.n_tma];
   if (warp >= p.tma_warps) {
     // ---- LDG warps: the table's non-bulk jobs (tiles [tma_total, total)) ----
-    const uint32_t total = p.tile_start[p.njobs];
-    const uint32_t nthr = (kHybridWarps - p.tma_warps) * 32;
-    const uint32_t tid = threadIdx.x - p.tma_warps * 32;
-    uint32_t j = p.n_tma;
-    for (uint32_t t = tma_total + blockIdx.x; t < total; t += gridDim.x) {
-      j = seek_job(p, t, j, p.njobs);
-      const mb_copy_job job = p.jobs[j];
-      run_tile(job, p.mode[j], p.aux[j], t - p.tile_start[j], tid, nthr);
-    }
+    ldg_tiles(p, tma_total, p.tile_start[p.njobs], p.n_tma, threadIdx.x - p.tma_warps * 32,
+              (kHybridWarps - p.tma_warps) * 32);
     return;
   }
   if (lane != 0) return;  // one elected lane per warp drives its own independent ring
@@ -397,15 +421,28 @@ __device__ __forceinline__ void hybrid_body(const P& p) {
 
   const uint32_t nworkers = gridDim.x * p.tma_warps;
   const uint32_t w = blockIdx.x * p.tma_warps + warp;
-  if (w >= tma_total) return;
-  const uint32_t mine = (tma_total - w + nworkers - 1) / nworkers;  // tiles w, w+nworkers, ...
+  // Tile i of worker w.  Strided (w, w + nworkers, ...): neighbouring workers stream neighbouring tiles -- the tuned
+  // layout for the few big jobs of an inline table.  Contiguous (a private span per worker): a worker stays inside one
+  // job for many tiles, so a device-resident table of hundreds of jobs is consulted once per job, not once per tile.
+  uint32_t first, step, mine;
+  if (p.tma_contig) {
+    const uint32_t per = (tma_total + nworkers - 1) / nworkers;
+    first = w * per;
+    step = 1;
+    mine = first < tma_total ? min(per, tma_total - first) : 0;
+  } else {
+    first = w;
+    step = nworkers;
+    mine = w < tma_total ? (tma_total - w + nworkers - 1) / nworkers : 0;
+  }
+  if (mine == 0) return;
 
   // Loads run (stages - stores) tiles ahead of the stores.
   const uint32_t ahead = stages - stores;
   uint32_t issued = 0, ld_stage = 0;
-  uint32_t ld_cursor = 0, st_cursor = 0;  // job cursors of the load stream and of the store stream
+  TmaCursor ld_cursor, st_cursor;  // the load stream and the store stream each remember the job they are in
   auto issue_load = [&]() {
-    const TmaTile tl = tma_decode(p, w + issued * nworkers, ld_cursor);
+    const TmaTile tl = tma_decode(p, first + issued * step, ld_cursor);
     mbar_expect_tx(&full[warp][ld_stage], tl.bytes);
     bulk_g2s(ring + (size_t)ld_stage * tile, tl.src, tl.bytes, &full[warp][ld_stage]);
     ++issued;
@@ -414,7 +451,7 @@ __device__ __forceinline__ void hybrid_body(const P& p) {
   while (issued < mine && issued < ahead) issue_load();
   uint32_t st_stage = 0, parity = 0;
   for (uint32_t k = 0; k < mine; ++k) {
-    const TmaTile tl = tma_decode(p, w + k * nworkers, st_cursor);
+    const TmaTile tl = tma_decode(p, first + k * step, st_cursor);
     mbar_wait(&full[warp][st_stage], parity);
     bulk_s2g(tl.dst, ring + (size_t)st_stage * tile, tl.bytes);
     if (++st_stage == stages) {
@@ -455,6 +492,7 @@ struct CopyTuning {
   uint32_t tma_warps;     // ring-driving warps per CTA (the other 8 - tma_warps warps run the LDG path)
   uint64_t tma_min_bytes; // auto: use the hybrid kernel when the bulk class carries at least this much
   int host_src_ctas;      // LDG grid cap when a table reads host-mapped memory (PCIe-bound)
+  int inline_contig, table_contig;  // ring workers: contiguous tile spans (1) or strided tiles (0)
 };
 
 const CopyTuning& tuning() {
@@ -471,6 +509,8 @@ const CopyTuning& tuning() {
     if (c.tma_stores >= c.tma_stages) c.tma_stores = c.tma_stages - 1;
     c.tma_min_bytes = (uint64_t)env_long("MB_TMA_MIN_BYTES", 1l << 20, 0, 1l << 40);
     c.host_src_ctas = (int)env_long("MB_COPY_HOST_SRC_CTAS", 64, 1, 4096);
+    c.inline_contig = (int)env_long("MB_TMA_INLINE_CONTIG", 0, 0, 1);
+    c.table_contig = (int)env_long("MB_TMA_TABLE_CONTIG", 1, 0, 1);
     return c;
   }();
   return t;
@@ -642,6 +682,7 @@ int launch_chunk(const mb_copy_job* jobs, int n, int src_kind, cudaStream_t stre
   p.tma_warps = (uint16_t)tn.tma_warps;
   p.tma_stages = (uint8_t)tn.tma_stages;
   p.tma_stores = (uint8_t)tn.tma_stores;
+  p.tma_contig = (uint8_t)tn.inline_contig;
   LaunchShape ls;
   rc = launch_shape(plan, 0, &ls);
   if (rc) return rc;
@@ -762,26 +803,31 @@ int mb_copy2d_table(mb_copy_ctx* c, const mb_copy_job* jobs, int njobs, int src_
     mb_copy_ctx::Slot& sl = c->slot[c->next];
     c->next = (c->next + 1) % mb_copy_ctx::kDepth;
     if (sl.used) MB_CUDA(cudaEventSynchronize(sl.done));  // the upload that last used this pinned slot has finished
+    // the four arrays are packed for THIS table's length, so the upload is ~57 bytes per job and nothing else
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t off_tile = up((size_t)n * sizeof(mb_copy_job));
+    const size_t off_aux = off_tile + up(((size_t)n + 1) * 4);
+    const size_t off_mode = off_aux + up((size_t)n * 4);
     TablePlan plan;
     int rc = build_table(jobs + first, n, src_kind, reinterpret_cast<mb_copy_job*>(sl.host),
-                         reinterpret_cast<uint32_t*>(sl.host + c->off_tile), reinterpret_cast<uint32_t*>(sl.host + c->off_aux),
-                         sl.host + c->off_mode, c->scratch, &plan);
+                         reinterpret_cast<uint32_t*>(sl.host + off_tile), reinterpret_cast<uint32_t*>(sl.host + off_aux),
+                         sl.host + off_mode, c->scratch, &plan);
     if (rc) return rc;
     if (plan.njobs == 0) continue;
-    // one upload: [jobs | tile_start | aux | mode] up to the last byte in use
-    const size_t upload = c->off_mode + plan.njobs;
+    const size_t upload = off_mode + plan.njobs;
     MB_CUDA(cudaMemcpyAsync(sl.dev, sl.host, upload, cudaMemcpyHostToDevice, stream));
     CopyParamsG p;
     p.jobs = reinterpret_cast<const mb_copy_job*>(sl.dev);
-    p.tile_start = reinterpret_cast<const uint32_t*>(sl.dev + c->off_tile);
-    p.aux = reinterpret_cast<const uint32_t*>(sl.dev + c->off_aux);
-    p.mode = sl.dev + c->off_mode;
+    p.tile_start = reinterpret_cast<const uint32_t*>(sl.dev + off_tile);
+    p.aux = reinterpret_cast<const uint32_t*>(sl.dev + off_aux);
+    p.mode = sl.dev + off_mode;
     p.njobs = plan.njobs;
     p.n_tma = plan.n_tma;
     p.tma_tile = tn.tma_tile;
     p.tma_warps = (uint16_t)tn.tma_warps;
     p.tma_stages = (uint8_t)tn.tma_stages;
     p.tma_stores = (uint8_t)tn.tma_stores;
+    p.tma_contig = (uint8_t)tn.table_contig;
     LaunchShape ls;
     rc = launch_shape(plan, 1, &ls);
     if (rc) return rc;
