@@ -576,6 +576,7 @@ class UnrollBatcher {
   NestPlan outPlan_, xoutPlan_;
   std::optional<py::object> outKey_;
   CopyQueue q_;
+  std::vector<uint8_t> srcOk_;  // [t][leaf]: 0 = ATen copy, 1 = device source, 2 = pinned host source
 
   void emit(std::vector<py::object>& finished) {
     const std::vector<torch::Tensor>& first = held_[0];
@@ -601,27 +602,77 @@ class UnrollBatcher {
               "dimension (" + std::to_string(catDim_) + "). Got " + std::to_string(n) + " and " + std::to_string(t.size(catDim_)));
       }
     }
+    // what the kernels may read directly, decided once per (step, leaf) -- not once per piece
+    const size_t L = first.size();
+    srcOk_.assign((size_t)T_ * L, 0);
+    for (int64_t t = 0; t < T_; ++t)
+      for (size_t i = 0; i < L; ++i) {
+        bool hostSrc = false;
+        const torch::Tensor& src = held_[(size_t)t][i];
+        const int dev = device_.is_cuda() ? (device_.has_index() ? (int)device_.index() : (int)c10::cuda::current_device()) : -1;
+        if (dev >= 0 && CopyQueue::readable(src, dev, &hostSrc)) srcOk_[(size_t)t * L + i] = hostSrc ? 2 : 1;
+      }
     int64_t taken = 0;
+    if (!open_ && n > 0 && n % B_ == 0 && alignedOk(first)) {
+      // Aligned unroll (the actor batch is a whole number K of learner batches and the batch dimension is outermost):
+      // the K batches of a leaf are slices of ONE allocation [K, T, B', ...], so a whole step of a leaf is ONE pitched
+      // copy with K rows -- T x leaves jobs instead of T x leaves x K.
+      const int64_t K = n / B_;
+      std::vector<torch::Tensor> big;
+      for (size_t i = 0; i < L; ++i) {
+        std::vector<int64_t> sz(first[i].sizes().begin(), first[i].sizes().end());
+        sz[0] = B_;
+        sz.insert(sz.begin(), {K, T_});
+        big.push_back(torch::empty(sz, first[i].options().device(device_)));
+        const int64_t inner = big[i].element_size() * prod(big[i].sizes(), 3, (size_t)big[i].dim());
+        const int dev = big[i].get_device();
+        mb_copy_job j;
+        j.rows = (uint64_t)K;
+        j.row_bytes = (uint64_t)(B_ * inner);
+        j.src_pitch = B_ * inner;
+        j.dst_pitch = T_ * B_ * inner;
+        for (int64_t t = 0; t < T_; ++t) {
+          const torch::Tensor& src = held_[(size_t)t][i];
+          const uint8_t ok = srcOk_[(size_t)t * L + i];
+          if (ok) {
+            if (j.row_bytes == 0) continue;
+            j.src = src.data_ptr();
+            j.dst = static_cast<char*>(big[i].data_ptr()) + t * B_ * inner;
+            q_.add(j, ok == 2, dev);
+          } else {
+            big[i].select(1, t).copy_(src.view(big[i].select(1, t).sizes()), /*non_blocking=*/true);
+          }
+        }
+      }
+      for (int64_t k = 0; k < K; ++k) {
+        openBatch(first, xleaves, /*allocate=*/false);
+        for (size_t i = 0; i < L; ++i) out_.push_back(big[i].select(0, k));
+        for (size_t i = 0; i < xleaves.size(); ++i) addCatCopy(q_, xout_[i], xgeom_[i], catDim_, 0, xleaves[i], k * B_, B_);
+        finished.push_back(closeBatch());
+      }
+      taken = n;
+    }
     while (taken < n) {
       if (!open_) openBatch(first, xleaves);
       const int64_t take = std::min(n - taken, B_ - fill_);
-      for (size_t i = 0; i < first.size(); ++i) {
+      for (size_t i = 0; i < L; ++i) {
         // step t of leaf i: out[i][t].narrow(ci, fill, take) <- item_t.narrow(ci, taken, take)
         const LeafGeom& g = geom_[i];
         const int64_t stepBytes = g.outer * g.dstCount * g.inner;
+        char* const dstBase = static_cast<char*>(out_[i].data_ptr()) + fill_ * g.inner;
+        mb_copy_job j;
+        j.rows = (uint64_t)g.outer;
+        j.row_bytes = (uint64_t)(take * g.inner);
+        j.src_pitch = n * g.inner;
+        j.dst_pitch = g.dstCount * g.inner;
         for (int64_t t = 0; t < T_; ++t) {
           const torch::Tensor& src = held_[(size_t)t][i];
-          bool hostSrc = false;
-          if (g.kernel && CopyQueue::readable(src, g.device, &hostSrc)) {
-            if (take * g.inner * g.outer == 0) continue;
-            mb_copy_job j;
+          const uint8_t ok = srcOk_[(size_t)t * L + i];
+          if (g.kernel && ok) {
+            if (j.rows * j.row_bytes == 0) continue;
             j.src = static_cast<const char*>(src.data_ptr()) + taken * g.inner;
-            j.dst = static_cast<char*>(out_[i].data_ptr()) + t * stepBytes + fill_ * g.inner;
-            j.rows = (uint64_t)g.outer;
-            j.row_bytes = (uint64_t)(take * g.inner);
-            j.src_pitch = n * g.inner;
-            j.dst_pitch = g.dstCount * g.inner;
-            q_.add(j, hostSrc, g.device);
+            j.dst = dstBase + t * stepBytes;
+            q_.add(j, ok == 2, g.device);
           } else {
             out_[i].select(0, t).narrow(ci, fill_, take).copy_(src.narrow(ci, taken, take), /*non_blocking=*/true);
           }
@@ -637,12 +688,21 @@ class UnrollBatcher {
     extra_.reset();
   }
 
-  void openBatch(const std::vector<torch::Tensor>& first, const std::vector<torch::Tensor>& xleaves) {
+  // the aligned fast path needs: a CUDA destination, the batch dimension outermost in every item, kernel-readable sources
+  bool alignedOk(const std::vector<torch::Tensor>& first) const {
+    if (catDim_ != 1 || !device_.is_cuda() || first.empty()) return false;
+    for (uint8_t ok : srcOk_)
+      if (!ok) return false;
+    return true;
+  }
+
+  void openBatch(const std::vector<torch::Tensor>& first, const std::vector<torch::Tensor>& xleaves, bool allocate = true) {
     out_.clear();
     geom_.clear();
     xout_.clear();
     xgeom_.clear();
     for (auto& t : first) {
+      if (!allocate) break;
       std::vector<int64_t> s(t.sizes().begin(), t.sizes().end());
       s[catDim_ - 1] = B_;
       s.insert(s.begin(), T_);

@@ -35,16 +35,22 @@ for r in range(a.reps):
     for it in steps[:-1]:
         ub.stack(it)
     flush.zero_()
+    torch.cuda._sleep(2_000_000)   # ~1 ms of GPU work queued: the host-side preparation of the launch is hidden, as in the loop
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _C.kernel_launches()
+    import time as _t
+    h0 = _t.perf_counter()
     s.record(); ub.stack(steps[-1]); e.record()
+    host_us = (_t.perf_counter() - h0) * 1e6
     torch.cuda.synchronize()
     assert _C.kernel_launches() - l0 == 1
     while not ub.empty():
         ub.get()
     if r >= 2:
         ts.append(s.elapsed_time(e) * 1e3)
+        res.setdefault("host_us", []).append(round(host_us, 1))
 ts.sort()
+res["host_us"] = sorted(res["host_us"])[len(res["host_us"]) // 2]
 res["gather_us_p50"] = round(ts[len(ts) // 2], 1)
 res["gather_gbs"] = round(2 * payload / ts[len(ts) // 2] / 1e3, 1)
 # the two-pass path: T stack launches + one cat launch
@@ -52,6 +58,7 @@ t_stack, t_cat = [], []
 for r in range(a.reps):
     steps = pool[r % 3]
     flush.zero_()
+    torch.cuda._sleep(2_000_000)
     s, m, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     s.record()
     for it in steps:
