@@ -73,11 +73,12 @@ typedef struct mb_copy_job {
   int64_t dst_pitch; /* bytes */
 } mb_copy_job;
 
-/* Max jobs carried inline in the kernel parameter block of one launch; larger tables are split into several
- * launches by mb_copy2d_batch. */
-#define MB_COPY_MAX_INLINE_JOBS 64
+/* Max jobs carried inline in the kernel parameters of one launch (<= 64: the classic 4 KiB parameter block; <= 512: the
+ * 32 KiB parameter space of CUDA 12.1+); larger tables are split into several launches by mb_copy2d_batch, or uploaded
+ * once and read from device memory by mb_copy2d_table. */
+#define MB_COPY_MAX_INLINE_JOBS 512
 
-/* Execute `njobs` pitched copies in as few launches as possible (one per 64 jobs).  `jobs` is a HOST array, read
+/* Execute `njobs` pitched copies in as few launches as possible (one per 512 jobs).  `jobs` is a HOST array, read
  * before the call returns.  Overlapping src/dst between jobs is undefined.  Returns the number of kernel launches
  * (>= 0) or a negative error. */
 MB_API int mb_copy2d_batch(const mb_copy_job* jobs, int njobs, mb_stream_t stream);

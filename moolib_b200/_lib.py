@@ -15,7 +15,7 @@ MB_AR_MAX_WORLD = 8
 MB_AR_MAX_SLOTS = 4
 MB_AR_BUFS_PER_SLOT = 3
 MB_AR_SHORT = 1
-MB_COPY_MAX_INLINE_JOBS = 64
+MB_COPY_MAX_INLINE_JOBS = 512
 MB_SRC_UNKNOWN, MB_SRC_DEVICE, MB_SRC_HOST_MAPPED = 0, 1, 2
 
 # every symbol include/moolib_b200.h declares (tests check the .so exports all of them)

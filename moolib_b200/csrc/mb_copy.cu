@@ -25,7 +25,8 @@ namespace {
 
 constexpr int kCopyThreads = 256;
 constexpr uint32_t kTileBytes = 16384;  // = kCopyThreads * 4 * 16 B: one unrolled-by-4 pass per full tile
-constexpr int kMaxJobs = MB_COPY_MAX_INLINE_JOBS;
+constexpr int kMaxJobs = MB_COPY_MAX_INLINE_JOBS;   // tables up to this length travel in the kernel parameters
+constexpr int kSmallJobs = 64;                        // ... in the classic 4 KiB parameter block when they are short
 
 enum : uint8_t {
   kModeBigRows = 0,      // row_bytes >= kTileBytes: a tile is a contiguous span inside one row
@@ -34,11 +35,14 @@ enum : uint8_t {
   kModeTma = 3           // bulk-async class: a tile is <= tma_tile bytes inside one row (jobs [0, n_tma))
 };
 
-struct CopyParams {
-  mb_copy_job jobs[kMaxJobs];
-  uint32_t tile_start[kMaxJobs + 1];  // exclusive prefix sum of tiles per job
-  uint32_t aux[kMaxJobs];             // big rows: tiles per row; small rows: rows per tile
-  uint8_t mode[kMaxJobs];
+// CAP = 64: fits the 4 KiB parameter block (cheapest launch: the per-item stack/cat launches).  CAP = 512: the large
+// (32764-byte) parameter space of CUDA 12.1+ -- a whole aligned unroll gather (T x leaves = 147 jobs) needs no upload.
+template <int CAP>
+struct CopyParamsT {
+  mb_copy_job jobs[CAP];
+  uint32_t tile_start[CAP + 1];  // exclusive prefix sum of tiles per job
+  uint32_t aux[CAP];             // big rows: tiles per row; small rows: rows per tile
+  uint8_t mode[CAP];
   uint32_t njobs;
   uint32_t n_tma;      // jobs [0, n_tma) are the bulk-async class (hybrid kernel only)
   uint32_t tma_tile;   // bytes per bulk copy
@@ -47,7 +51,10 @@ struct CopyParams {
   uint8_t tma_stores;  // store groups allowed to be still reading shared memory
   uint8_t tma_contig;  // tile assignment of the ring workers: 0 strided, 1 contiguous spans
 };
+using CopyParams = CopyParamsT<kSmallJobs>;
+using CopyParamsL = CopyParamsT<kMaxJobs>;
 static_assert(sizeof(CopyParams) <= 4000, "CopyParams must fit the 4 KiB kernel parameter block");
+static_assert(sizeof(CopyParamsL) <= 32764, "CopyParamsL must fit the large kernel parameter space");
 
 // The same table in DEVICE memory (mb_copy2d_table): any number of jobs in one launch.  Uploaded once per launch by
 // one async copy from the context's pinned staging; the kernels read it through L1/L2.
@@ -270,6 +277,7 @@ __device__ __forceinline__ void ldg_body(const P& p) {
   ldg_tiles(p, 0, p.tile_start[p.njobs], 0, threadIdx.x, kCopyThreads);
 }
 __global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_kernel(const __grid_constant__ CopyParams p) { ldg_body(p); }
+__global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_kernel_l(const __grid_constant__ CopyParamsL p) { ldg_body(p); }
 __global__ void __launch_bounds__(kCopyThreads, 4) copy2d_ldg_table_kernel(const CopyParamsG p) { ldg_body(p); }
 
 // Pointer-array gather (uniform rows, DEVICE-resident row pointers): K-B1 / K-B4.
@@ -470,6 +478,9 @@ __device__ __forceinline__ void hybrid_body(const P& p) {
 __global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_kernel(const __grid_constant__ CopyParams p) {
   hybrid_body(p);
 }
+__global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_kernel_l(const __grid_constant__ CopyParamsL p) {
+  hybrid_body(p);
+}
 __global__ void __launch_bounds__(kHybridWarps * 32, 1) copy2d_hybrid_table_kernel(const CopyParamsG p) { hybrid_body(p); }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -532,7 +543,7 @@ int validate_job(const mb_copy_job& j, int i) {
 }
 
 std::mutex g_attr_mu;
-uint32_t g_hybrid_smem_set[2] = {0, 0};  // [inline kernel, table kernel]
+uint32_t g_hybrid_smem_set[3] = {0, 0, 0};  // [inline kernel, table kernel, large inline kernel]
 
 // Where the caller says the sources live (MB_SRC_*); UNKNOWN asks the driver per job.
 bool source_is_device(const mb_copy_job& j, int src_kind) {
@@ -648,8 +659,10 @@ int launch_shape(const TablePlan& plan, int which_kernel, LaunchShape* out) {
       if (g_hybrid_smem_set[which_kernel] < smem) {
         if (which_kernel == 0)
           MB_CUDA(cudaFuncSetAttribute(copy2d_hybrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else
+        else if (which_kernel == 1)
           MB_CUDA(cudaFuncSetAttribute(copy2d_hybrid_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+          MB_CUDA(cudaFuncSetAttribute(copy2d_hybrid_kernel_l, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_hybrid_smem_set[which_kernel] = smem;
       }
     }
@@ -667,10 +680,11 @@ int launch_shape(const TablePlan& plan, int which_kernel, LaunchShape* out) {
   return MB_OK;
 }
 
-int launch_chunk(const mb_copy_job* jobs, int n, int src_kind, cudaStream_t stream) {
+template <class PT>
+int launch_inline(const mb_copy_job* jobs, int n, int src_kind, int which_kernel, void (*ldg)(const PT), void (*hyb)(const PT),
+                  cudaStream_t stream) {
   const CopyTuning& tn = tuning();
-  CopyParams p;
-  std::memset(&p, 0, sizeof(p));
+  static thread_local PT p;  // 29 KiB for the large variant: not on the stack of a Python thread
   static thread_local std::vector<uint8_t> scratch;
   TablePlan plan;
   int rc = build_table(jobs, n, src_kind, p.jobs, p.tile_start, p.aux, p.mode, scratch, &plan);
@@ -682,14 +696,19 @@ int launch_chunk(const mb_copy_job* jobs, int n, int src_kind, cudaStream_t stre
   p.tma_warps = (uint16_t)tn.tma_warps;
   p.tma_stages = (uint8_t)tn.tma_stages;
   p.tma_stores = (uint8_t)tn.tma_stores;
-  p.tma_contig = (uint8_t)tn.inline_contig;
+  p.tma_contig = (uint8_t)(which_kernel == 2 ? tn.table_contig : tn.inline_contig);
   LaunchShape ls;
-  rc = launch_shape(plan, 0, &ls);
+  rc = launch_shape(plan, which_kernel, &ls);
   if (rc) return rc;
-  if (plan.hybrid) copy2d_hybrid_kernel<<<ls.grid, kHybridWarps * 32, ls.smem, stream>>>(p);
-  else copy2d_ldg_kernel<<<ls.grid, kCopyThreads, 0, stream>>>(p);
+  if (plan.hybrid) hyb<<<ls.grid, kHybridWarps * 32, ls.smem, stream>>>(p);
+  else ldg<<<ls.grid, kCopyThreads, 0, stream>>>(p);
   MB_CUDA(cudaGetLastError());
   return 1;
+}
+
+int launch_chunk(const mb_copy_job* jobs, int n, int src_kind, cudaStream_t stream) {
+  if (n <= kSmallJobs) return launch_inline<CopyParams>(jobs, n, src_kind, 0, copy2d_ldg_kernel, copy2d_hybrid_kernel, stream);
+  return launch_inline<CopyParamsL>(jobs, n, src_kind, 2, copy2d_ldg_kernel_l, copy2d_hybrid_kernel_l, stream);
 }
 
 }  // namespace
