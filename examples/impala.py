@@ -119,6 +119,9 @@ class Flags:
     obs_pool: int = 8                 # distinct pre-generated observation slabs per buffer (defeats caching)
     max_queued_batches: int = 8       # back-pressure on the actor side: one time batch ahead (8 x 19 MB)
     fused_batcher: bool = True        # moolib_b200 only: UnrollBatcher (stack x T fused with cat, one launch per unroll)
+    paced_actor: bool = True          # at most ceil(actor steps per learner batch) actor steps between two learner steps
+                                      # while learner batches are queued: the GPU sees an even mix instead of bursts of
+                                      # ~20 actor steps, so the lock-step of N learners does not wait on one peer's burst
     seed: int = 1234
 
 
@@ -234,6 +237,10 @@ class LearnerLoop:
         self.learn_batcher = api.Batcher(flags.batch_size, flags.device, dim=1)
         self.learn_sources = [s.unroll for s in self.env_states] if self.fused else [self.learn_batcher]
         self._next_source = 0
+        # one unroll (unroll_length new actor steps) yields actor_batch_size / batch_size learner batches
+        per_batch = flags.unroll_length * flags.batch_size / max(flags.actor_batch_size, 1)
+        self.actor_budget = max(1, int(-(-per_batch // 1)))
+        self.actor_since_learn = 0
         self.res = LearnerResult()
         self.next_env_index = 0
         self.grad_norm_dev = torch.zeros((), device=self.device)
@@ -279,16 +286,20 @@ class LearnerLoop:
             self.res.last_loss = compute_gradients(model, self.learn_get(), flags)
             self.res.env_train_steps += flags.unroll_length * flags.batch_size
             acc.reduce_gradients(flags.batch_size)
+            self.actor_since_learn = 0
             self.res.n_learn += 1
             self.res.t_learn += time.perf_counter() - t_tick
             return False
         if acc.wants_gradients():
             acc.skip_gradients()
             self.res.n_skip += 1
-        if self.learn_size() >= self.flags.max_queued_batches:
+        queued = self.learn_size()
+        if queued >= self.flags.max_queued_batches or (
+                flags.paced_actor and queued > 0 and self.actor_since_learn >= self.actor_budget):
             # (not in the reference loop) never let unconsumed learner batches pile up in device memory while the
-            # accumulator is not asking for gradients
-            time.sleep(0.0002)
+            # accumulator is not asking for gradients, and do not enqueue a burst of actor steps ahead of the next
+            # optimizer / learner step either
+            time.sleep(0.0001)
             self.res.n_idle += 1
             self.res.t_idle += time.perf_counter() - t_tick
             return False
@@ -313,6 +324,7 @@ class LearnerLoop:
         del cpu_env_outputs
         es.future = self.envs.step(cur, action)
         self.res.actor_steps += 1
+        self.actor_since_learn += 1
         last_data = {"env_outputs": env_outputs, "actor_outputs": actor_outputs}
         if self.fused:
             es.count += 1
