@@ -219,6 +219,8 @@ class GroupService {
   void onResult(const std::string& src, const Bytes& payload);
   void tryFinish(const std::shared_ptr<SmallReduce>& r);
   bool feed(const std::string& opName, uint32_t syncId, size_t index, const Bytes& value);
+  void feedOp(const std::shared_ptr<SmallReduce>& r, size_t index, const Bytes& value);
+  std::shared_ptr<SmallReduce> liveOpLocked(const std::string& opName, uint32_t syncId);
 
   std::shared_ptr<RpcCore> rpc_;
   std::mutex mu_;

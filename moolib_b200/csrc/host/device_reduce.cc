@@ -166,19 +166,22 @@ uint64_t sizeClass(uint64_t bytes) {
   return c;
 }
 
-// group.all_reduce on a CUDA tensor: [connect] -> [gate: everyone called] -> stage + allreduce kernels -> event.
+// group.all_reduce on a CUDA tensor: [connect once per (name, size class)] -> stage + device gate + reduce kernels -> event.
+// "Everyone has called" is established by the gate kernel (K-A0) over NVLink, not by a control-plane round trip: the
+// call costs three launches, and a peer that never calls surfaces as the reference's "AllReduce operation timed out".
+// Every operation NAME owns its context (its own epochs, flags and result block): two differently named operations in
+// flight can be launched in different orders on different ranks without pairing the wrong tensors.
 struct TensorReduceOp {
   std::shared_ptr<GroupService> service;
   std::shared_ptr<GroupInfo> info;
   std::shared_ptr<DeviceReducer> reducer;
   std::shared_ptr<FutureState> state;
-  std::shared_ptr<SmallReduce> gate;
   std::string name;
   torch::Tensor tensor, flat;
   c10::cuda::CUDAStream stream;
   cudaEvent_t event = nullptr;
   uint32_t syncId = 0;
-  int phase = 0;  // 0 connecting, 1 gating, 2 kernels in flight, 3 finished
+  int phase = 0;  // 0 connecting, 2 kernels in flight, 3 finished
   Clock::time_point start = Clock::now();
 
   TensorReduceOp(c10::cuda::CUDAStream s) : stream(s) {}
@@ -202,24 +205,6 @@ struct TensorReduceOp {
             return fail("AllReduce operation timed out");
           return;
         }
-        Writer w;
-        w.u64(1);
-        gate = service->allReduce(info, "gate/" + name, w.b, [](const Bytes& a, const Bytes& b) {
-          Reader ra(a), rb(b);
-          Writer o;
-          o.u64(ra.u64() + rb.u64());
-          return o.b;
-        });
-        phase = 1;
-      }
-      if (phase == 1) {
-        auto& g = *gate->future;
-        if (!g.done()) return;
-        {
-          std::string err;
-          if (!(g.snapshot(nullptr, &err) & 1)) return fail(err.empty() ? "AllReduce operation cancelled" : err);
-        }
-        // everyone is here: one stage launch + one allreduce launch on the caller's stream
         c10::cuda::CUDAGuard dg(reducer->device());
         flat = tensor.is_contiguous() ? tensor : tensor.contiguous();
         const float* src = flat.data_ptr<float>();
@@ -227,10 +212,10 @@ struct TensorReduceOp {
         mb_stream_t s = static_cast<mb_stream_t>(stream.stream());
         launch_counter() += check(mb_ar_stage(reducer->ctx(), 0, &src, &numel, 1, 0, 0, s), "mb_ar_stage");
         mb_ar_hdr hdr{1, 0, 1, 1};
-        launch_counter() += check(mb_ar_allreduce(reducer->ctx(), 0, &hdr, nullptr, nullptr, 0, flat.data_ptr<float>(),
-                                                  numel, /*scale=*/0, MB_AR_ALGO_AUTO,
-                                                  (uint32_t)(service->rpc()->getTimeout() * 1000), s),
-                                  "mb_ar_allreduce");
+        launch_counter() += check(mb_ar_reduce_gated(reducer->ctx(), 0, &hdr, /*min_batch=*/0, nullptr, nullptr, 0,
+                                                     flat.data_ptr<float>(), numel, /*scale=*/0, MB_AR_ALGO_AUTO,
+                                                     (uint32_t)(service->rpc()->getTimeout() * 1000), s),
+                                  "mb_ar_reduce_gated");
         if (!flat.is_same(tensor)) tensor.copy_(flat, true);
         if (cudaEventCreateWithFlags(&event, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventRecord(event, stream.stream()) != cudaSuccess)
@@ -245,6 +230,7 @@ struct TensorReduceOp {
         mb_ar_result(reducer->ctx(), 0, nullptr, &status);
         if (status == MB_ETIMEOUT) return fail("AllReduce operation timed out");
         if (status != 0) return fail("moolib_b200: allreduce kernel failed with status " + std::to_string(status));
+        check(mb_ar_slot_advance(reducer->ctx(), 0), "mb_ar_slot_advance");
         phase = 3;
         state->setResult(Bytes());
       }
@@ -274,7 +260,16 @@ std::shared_ptr<PyFuture> DeviceReducerSet::allReduceTensor(const std::string& n
     if (std::find(m.begin(), m.end(), service_->rpc()->getName()) == m.end())
       throw std::runtime_error("AllReduce: local peer is not a member of the specified group!");
   }
-  op->reducer = get("ar", device, sizeClass((uint64_t)t.numel() * 4 + 64), 1);
+  // at most one operation per name is in flight (GroupService rejects "all-reduce twice concurrently"); the name is
+  // part of the context key so that differently named operations never share epochs
+  op->reducer = get("ar:" + name, device, sizeClass((uint64_t)t.numel() * 4 + 64), 1);
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    auto& slot = inflight_[name];
+    if (auto prev = slot.lock())
+      if (!prev->done()) throw std::runtime_error("Attempt to all-reduce twice concurrently with the name '" + name + "'");
+    slot = op->state;
+  }
   auto fut = std::make_shared<PyFuture>();
   fut->state = op->state;
   fut->ready = std::move(pyTensor);  // in place, like the reference (test/test_reduce.py:56)

@@ -72,6 +72,7 @@ class DeviceReducerSet {
   std::shared_ptr<GroupInfo> info_;
   std::mutex mu_;
   std::map<std::string, std::shared_ptr<DeviceReducer>> reducers_;
+  std::map<std::string, std::weak_ptr<FutureState>> inflight_;  // all_reduce on CUDA tensors, by operation name
 };
 
 struct GroupParts {

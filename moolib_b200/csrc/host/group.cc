@@ -257,34 +257,49 @@ std::shared_ptr<SmallReduce> GroupService::allReduce(std::shared_ptr<GroupInfo> 
   return r;
 }
 
+// Look the operation up; returns it only if a contribution for (opName, syncId) can be fed into it right now.
+// Caller holds mu_.
+std::shared_ptr<SmallReduce> GroupService::liveOpLocked(const std::string& opName, uint32_t syncId) {
+  auto i = ops_.find(opName);
+  if (i == ops_.end()) return nullptr;
+  std::shared_ptr<SmallReduce> r = i->second.lock();
+  if (!r || r->syncId != syncId || r->future->done() || r->myIndex != 0) return nullptr;
+  return r;
+}
+
 bool GroupService::feed(const std::string& opName, uint32_t syncId, size_t index, const Bytes& value) {
   std::shared_ptr<SmallReduce> r;
   {
     std::lock_guard<std::mutex> l(mu_);
-    auto i = ops_.find(opName);
-    if (i != ops_.end()) r = i->second.lock();
+    r = liveOpLocked(opName, syncId);
   }
-  if (!r || r->syncId != syncId || r->future->done() || r->myIndex != 0) return false;
-  {
-    std::lock_guard<std::mutex> l(r->mu);
-    if (r->finished || index >= r->peers.size() || r->got.count(index)) return true;
-    r->got[index] = value;
-  }
-  tryFinish(r);
+  if (!r) return false;
+  feedOp(r, index, value);
   return true;
 }
 
+void GroupService::feedOp(const std::shared_ptr<SmallReduce>& r, size_t index, const Bytes& value) {
+  {
+    std::lock_guard<std::mutex> l(r->mu);
+    if (r->finished || index >= r->peers.size() || r->got.count(index)) return;
+    r->got[index] = value;
+  }
+  tryFinish(r);
+}
+
 void GroupService::tryFinish(const std::shared_ptr<SmallReduce>& r) {
-  Bytes acc;
+  // Take the contributions out under the lock, reduce WITHOUT it: a Python `op` needs the GIL, and the thread that
+  // holds the GIL may be inside allReduce() waiting for r->mu (feed -> tryFinish) -- reducing under r->mu deadlocked.
+  std::map<size_t, Bytes> got;
   {
     std::lock_guard<std::mutex> l(r->mu);
     if (r->finished || r->got.size() != r->peers.size()) return;
     r->finished = true;
-    // fixed member order: ((v0 op v1) op v2) ...
-    acc = r->got[0];
-    for (size_t i = 1; i < r->peers.size(); ++i) acc = r->op(acc, r->got[i]);
-    r->got.clear();
+    got.swap(r->got);
   }
+  // fixed member order: ((v0 op v1) op v2) ...
+  Bytes acc = std::move(got[0]);
+  for (size_t i = 1; i < r->peers.size(); ++i) acc = r->op(acc, got[i]);
   Writer w;
   w.str(r->opName);
   w.u32(r->syncId);
@@ -299,10 +314,18 @@ void GroupService::onContribution(const std::string&, const Bytes& p) {
   uint32_t syncId = rd.u32();
   size_t index = (size_t)rd.u64();
   Bytes value = rd.str();
-  if (!feed(opName, syncId, index, value)) {
+  std::shared_ptr<SmallReduce> r;
+  {
+    // ONE critical section for "is the operation there?" and "park the contribution": allReduce() registers the op and
+    // scans early_ under the same mutex, so a contribution is either fed or found by that scan -- never stranded.
     std::lock_guard<std::mutex> l(mu_);
-    early_.push_back(Early{Clock::now(), std::move(opName), syncId, index, std::move(value)});
+    r = liveOpLocked(opName, syncId);
+    if (!r) {
+      early_.push_back(Early{Clock::now(), std::move(opName), syncId, index, std::move(value)});
+      return;
+    }
   }
+  feedOp(r, index, value);
 }
 
 void GroupService::onResult(const std::string&, const Bytes& p) {

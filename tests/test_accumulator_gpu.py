@@ -169,6 +169,16 @@ while not f.done():
 r = f.result()
 exact, _ = oracle.allreduce_rankorder([gen_input(900 + q, [64 * 64], 'f32') for q in range(world)], [(1, 0, 1)] * world, scale=False)
 assert r.data_ptr() == x.data_ptr() and x.cpu().numpy().reshape(-1).tobytes() == exact.tobytes()
+# two differently named operations in flight, started in OPPOSITE orders on odd and even ranks (round-1 advisor finding:
+# they must never pair the wrong tensors) -- every name owns its context
+xa = torch.full((5000,), float(rank + 1), device='cuda'); xb = torch.full((300,), float(10 * (rank + 1)), device='cuda')
+order = [('opA', xa), ('opB', xb)] if rank % 2 == 0 else [('opB', xb), ('opA', xa)]
+futs = [group.all_reduce(n_, t_) for n_, t_ in order]
+t0 = time.time()
+while not all(f_.done() for f_ in futs):
+    pump(); assert time.time() - t0 < 60
+for f_ in futs: f_.result()
+assert (xa == world * (world + 1) / 2).all().item() and (xb == 10 * world * (world + 1) / 2).all().item()
 # Accumulator rounds
 numels = [992, 31]
 offs, total = oracle.flat_layout(numels)
