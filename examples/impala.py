@@ -117,7 +117,7 @@ class Flags:
     host_obs: bool = True             # True: observations come from pinned host slabs (EnvPool format), H2D per step
     read_metrics: bool = True         # True: grad-norm .item() per optimizer step, as experiment.py:166 does
     obs_pool: int = 8                 # distinct pre-generated observation slabs per buffer (defeats caching)
-    max_queued_batches: int = 8       # back-pressure on the actor side: one time batch ahead (8 x 19 MB)
+    max_queued_batches: int = 24      # back-pressure on the actor side: both buffers' unrolls plus one (24 x 19 MB)
     fused_batcher: bool = True        # moolib_b200 only: UnrollBatcher (stack x T fused with cat, one launch per unroll)
     paced_actor: bool = True          # at most ceil(actor steps per learner batch) actor steps between two learner steps
                                       # while learner batches are queued: the GPU sees an even mix instead of bursts of

@@ -62,6 +62,21 @@ DeviceReducer::DeviceReducer(std::shared_ptr<GroupService> service, std::shared_
 
 DeviceReducer::~DeviceReducer() {
   if (ctx_) mb_ar_ctx_destroy(ctx_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+cudaStream_t DeviceReducer::stream() {
+  if (!stream_) {
+    c10::cuda::CUDAGuard g(device_);
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaGetLastError();
+      stream_ = nullptr;
+      throw std::runtime_error("moolib_b200: cannot create the reducer stream");
+    }
+  }
+  return stream_;
 }
 
 bool DeviceReducer::poll() {
@@ -178,8 +193,9 @@ struct TensorReduceOp {
   std::shared_ptr<FutureState> state;
   std::string name;
   torch::Tensor tensor, flat;
-  c10::cuda::CUDAStream stream;
-  cudaEvent_t event = nullptr;
+  c10::cuda::CUDAStream stream;  // the caller's stream: the tensor is produced / consumed there
+  cudaEvent_t ready = nullptr;   // caller's stream at call time: the tensor's contents are final
+  cudaEvent_t event = nullptr;   // the kernels on the reducer's own stream have finished
   uint32_t syncId = 0;
   int phase = 0;  // 0 connecting, 2 kernels in flight, 3 finished
   Clock::time_point start = Clock::now();
@@ -187,6 +203,7 @@ struct TensorReduceOp {
   TensorReduceOp(c10::cuda::CUDAStream s) : stream(s) {}
   ~TensorReduceOp() {
     if (event) cudaEventDestroy(event);
+    if (ready) cudaEventDestroy(ready);
   }
 
   void fail(const std::string& e) {
@@ -209,16 +226,19 @@ struct TensorReduceOp {
         flat = tensor.is_contiguous() ? tensor : tensor.contiguous();
         const float* src = flat.data_ptr<float>();
         uint64_t numel = (uint64_t)flat.numel();
-        mb_stream_t s = static_cast<mb_stream_t>(stream.stream());
+        // Own stream per operation name: a gate that waits for the peers must not block the caller's stream, nor sit
+        // in front of another operation's gate (two names started in opposite orders on two ranks would deadlock).
+        cudaStream_t side = reducer->stream();
+        if (ready) cudaStreamWaitEvent(side, ready, 0);
+        mb_stream_t s = static_cast<mb_stream_t>(side);
         launch_counter() += check(mb_ar_stage(reducer->ctx(), 0, &src, &numel, 1, 0, 0, s), "mb_ar_stage");
         mb_ar_hdr hdr{1, 0, 1, 1};
         launch_counter() += check(mb_ar_reduce_gated(reducer->ctx(), 0, &hdr, /*min_batch=*/0, nullptr, nullptr, 0,
                                                      flat.data_ptr<float>(), numel, /*scale=*/0, MB_AR_ALGO_AUTO,
                                                      (uint32_t)(service->rpc()->getTimeout() * 1000), s),
                                   "mb_ar_reduce_gated");
-        if (!flat.is_same(tensor)) tensor.copy_(flat, true);
         if (cudaEventCreateWithFlags(&event, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventRecord(event, stream.stream()) != cudaSuccess)
+            cudaEventRecord(event, side) != cudaSuccess)
           return fail("moolib_b200: cudaEventRecord failed");
         phase = 2;
       }
@@ -231,6 +251,12 @@ struct TensorReduceOp {
         if (status == MB_ETIMEOUT) return fail("AllReduce operation timed out");
         if (status != 0) return fail("moolib_b200: allreduce kernel failed with status " + std::to_string(status));
         check(mb_ar_slot_advance(reducer->ctx(), 0), "mb_ar_slot_advance");
+        // whatever the caller enqueues next on its stream sees the result
+        cudaStreamWaitEvent(stream.stream(), event, 0);
+        if (!flat.is_same(tensor)) {
+          c10::cuda::CUDAStreamGuard sg(stream);
+          tensor.copy_(flat, true);
+        }
         phase = 3;
         state->setResult(Bytes());
       }
@@ -253,6 +279,11 @@ std::shared_ptr<PyFuture> DeviceReducerSet::allReduceTensor(const std::string& n
   op->name = name;
   op->tensor = t;
   op->state = std::make_shared<FutureState>();
+  {
+    c10::cuda::CUDAGuard dg(device);
+    if (cudaEventCreateWithFlags(&op->ready, cudaEventDisableTiming) == cudaSuccess)
+      cudaEventRecord(op->ready, op->stream.stream());
+  }
   {
     std::lock_guard<std::mutex> l(info_->mutex);
     op->syncId = info_->syncId;

@@ -6,6 +6,7 @@
 #include "control.h"
 
 #include <c10/cuda/CUDAStream.h>
+#include <cuda_runtime_api.h>
 
 namespace mbh {
 
@@ -43,6 +44,9 @@ class DeviceReducer {
   int rank() const { return rank_; }
   int device() const { return device_; }
   uint64_t maxBytes() const { return maxBytes_; }
+  // The context's own stream: kernels that wait for peers (K-A0) must not sit in front of unrelated work -- or of
+  // another context's gate -- on the caller's stream.
+  cudaStream_t stream();
 
  private:
   std::shared_ptr<GroupService> service_;
@@ -57,6 +61,7 @@ class DeviceReducer {
   bool connected_ = false, failed_ = false;
   std::string error_;
   std::shared_ptr<SmallReduce> exchange_;
+  cudaStream_t stream_ = nullptr;
 };
 
 class DeviceReducerSet {
