@@ -181,23 +181,27 @@ uint64_t sizeClass(uint64_t bytes) {
   return c;
 }
 
-// group.all_reduce on a CUDA tensor: [connect once per (name, size class)] -> stage + device gate + reduce kernels -> event.
-// "Everyone has called" is established by the gate kernel (K-A0) over NVLink, not by a control-plane round trip: the
-// call costs three launches, and a peer that never calls surfaces as the reference's "AllReduce operation timed out".
-// Every operation NAME owns its context (its own epochs, flags and result block): two differently named operations in
-// flight can be launched in different orders on different ranks without pairing the wrong tensors.
+// group.all_reduce on a CUDA tensor: [connect once per (name, size class)] -> [control-plane gate: everyone has called and
+// has this name's peers mapped] -> stage + K-A0 + K-A2 on the context's own stream -> event.
+// Every operation NAME owns its context (its own epochs, flags, result block and stream): two differently named
+// operations in flight can be started in different orders on different ranks without pairing the wrong tensors or
+// queueing one gate kernel behind the other.  The control-plane gate stays (one round trip, like the reference's own
+// RPC-based all_reduce): a kernel that waits for its peers is only launched once every peer is past context creation and
+// cudaIpcOpenMemHandle for that name -- those calls synchronise the device, and a rank blocked in one of them behind its
+// own spinning gate could never launch the kernel the other rank's gate is waiting for.
 struct TensorReduceOp {
   std::shared_ptr<GroupService> service;
   std::shared_ptr<GroupInfo> info;
   std::shared_ptr<DeviceReducer> reducer;
   std::shared_ptr<FutureState> state;
+  std::shared_ptr<SmallReduce> gate;
   std::string name;
   torch::Tensor tensor, flat;
   c10::cuda::CUDAStream stream;  // the caller's stream: the tensor is produced / consumed there
   cudaEvent_t ready = nullptr;   // caller's stream at call time: the tensor's contents are final
   cudaEvent_t event = nullptr;   // the kernels on the reducer's own stream have finished
   uint32_t syncId = 0;
-  int phase = 0;  // 0 connecting, 2 kernels in flight, 3 finished
+  int phase = 0;  // 0 connecting, 1 gating, 2 kernels in flight, 3 finished
   Clock::time_point start = Clock::now();
 
   TensorReduceOp(c10::cuda::CUDAStream s) : stream(s) {}
@@ -221,6 +225,23 @@ struct TensorReduceOp {
           if (Clock::now() - start > std::chrono::duration<double>(service->rpc()->getTimeout()))
             return fail("AllReduce operation timed out");
           return;
+        }
+        Writer w;
+        w.u64(1);
+        gate = service->allReduce(info, "gate/" + name, w.b, [](const Bytes& a, const Bytes& b) {
+          Reader ra(a), rb(b);
+          Writer o;
+          o.u64(ra.u64() + rb.u64());
+          return o.b;
+        });
+        phase = 1;
+      }
+      if (phase == 1) {
+        auto& g = *gate->future;
+        if (!g.done()) return;
+        {
+          std::string err;
+          if (!(g.snapshot(nullptr, &err) & 1)) return fail(err.empty() ? "AllReduce operation cancelled" : err);
         }
         c10::cuda::CUDAGuard dg(reducer->device());
         flat = tensor.is_contiguous() ? tensor : tensor.contiguous();
