@@ -544,6 +544,10 @@ def run_reference(args):
     threads = max(1, min(cores, 32) // max(n_peers, world if multi else 1))
     torch.set_num_threads(threads)
     K, W = args.steps, args.warmup
+    if n_peers > 1:
+        # N CPU peers share this one process: a step costs N forward/backward passes on the host cores.  Keep the sample
+        # bounded: one warm-up step, then as many of the K steps as fit into --max-seconds.
+        W = min(W, 1)
     if multi:
         port = int(os.environ.get("MASTER_PORT", 29400)) + 41
     else:
