@@ -50,6 +50,7 @@ class ImpalaNet(nn.Module):
         core = 256 + num_actions + 1
         self.policy = nn.Linear(core, num_actions)
         self.baseline = nn.Linear(core, 1)
+        self.normalize = None  # optional fused u8 -> float/255 (moolib_b200.u8_to_float); None: x.float() / 255.0
 
     def initial_state(self, batch_size=1):
         return tuple()
@@ -57,7 +58,8 @@ class ImpalaNet(nn.Module):
     def forward(self, inputs, core_state=()):
         x = inputs["state"]
         T, B = x.shape[0], x.shape[1]
-        x = torch.flatten(x, 0, 1).float() / 255.0
+        x = torch.flatten(x, 0, 1)
+        x = self.normalize(x) if (self.normalize is not None and x.is_cuda) else x.float() / 255.0
         x = F.relu(self.stages(x)).reshape(T * B, -1)
         x = F.relu(self.fc(x))
         one_hot = F.one_hot(inputs["prev_action"].reshape(T * B), self.num_actions).float()
@@ -80,8 +82,11 @@ def action_log_probs(logits, actions):
 
 @torch.no_grad()
 def vtrace_targets(behavior_logits, target_logits, actions, discounts, rewards, values, bootstrap_value,
-                   clip_rho=1.0, clip_pg_rho=1.0):
+                   clip_rho=1.0, clip_pg_rho=1.0, fused=None):
     log_rhos = action_log_probs(target_logits, actions) - action_log_probs(behavior_logits, actions)
+    if fused is not None and log_rhos.is_cuda:
+        # moolib_b200.vtrace_from_importance_weights: the scan below as ONE kernel (bit-identical results)
+        return fused(log_rhos, discounts, rewards, values, bootstrap_value, clip_rho, clip_pg_rho)
     rhos = torch.exp(log_rhos)
     clipped_rhos = torch.clamp(rhos, max=clip_rho)
     cs = torch.clamp(rhos, max=1.0)
@@ -119,13 +124,14 @@ class Flags:
     obs_pool: int = 8                 # distinct pre-generated observation slabs per buffer (defeats caching)
     max_queued_batches: int = 24      # back-pressure on the actor side: both buffers' unrolls plus one (24 x 19 MB)
     fused_batcher: bool = True        # moolib_b200 only: UnrollBatcher (stack x T fused with cat, one launch per unroll)
+    fused_learner_ops: bool = True    # moolib_b200 only: V-trace scan + u8->float/255 as one kernel each
     paced_actor: bool = True          # at most ceil(actor steps per learner batch) actor steps between two learner steps
                                       # while learner batches are queued: the GPU sees an even mix instead of bursts of
                                       # ~20 actor steps, so the lock-step of N learners does not wait on one peer's burst
     seed: int = 1234
 
 
-def compute_gradients(model, data, flags):
+def compute_gradients(model, data, flags, fused_vtrace=None):
     """experiment.py:109-156"""
     env_outputs, actor_outputs = data["env_outputs"], data["actor_outputs"]
     model.train()
@@ -140,7 +146,7 @@ def compute_gradients(model, data, flags):
     discounts = (~env_outputs["done"]).float() * flags.discounting
     vs, pg_adv = vtrace_targets(actor_outputs["policy_logits"], learner_outputs["policy_logits"],
                                 actor_outputs["action"], discounts, rewards, learner_outputs["baseline"],
-                                bootstrap_value)
+                                bootstrap_value, fused=fused_vtrace)
     logits = learner_outputs["policy_logits"]
     policy, log_policy = F.softmax(logits, dim=-1), F.log_softmax(logits, dim=-1)
     entropy_loss = flags.entropy_cost * -torch.mean(torch.sum(-policy * log_policy, dim=-1))
@@ -220,6 +226,10 @@ class LearnerLoop:
         #   to_device     = EnvStepperFuture.result(device=...): all keys of a pinned result in one launch.
         self.fused = bool(flags.fused_batcher and hasattr(api, "UnrollBatcher"))
         self.to_device = getattr(api, "to_device", None)
+        #   vtrace_from_importance_weights / u8_to_float = the learner's V-trace scan and input normalisation, one launch each
+        self.fused_vtrace = getattr(api, "vtrace_from_importance_weights", None) if flags.fused_learner_ops else None
+        if flags.fused_learner_ops and hasattr(api, "u8_to_float"):
+            model.normalize = api.u8_to_float
         self.T = T
         self.env_states = []
         for _ in range(flags.num_actor_batches):
@@ -283,7 +293,7 @@ class LearnerLoop:
             self.res.t_opt += time.perf_counter() - t_tick
             return True
         if self.learn_size() and acc.wants_gradients():
-            self.res.last_loss = compute_gradients(model, self.learn_get(), flags)
+            self.res.last_loss = compute_gradients(model, self.learn_get(), flags, self.fused_vtrace)
             self.res.env_train_steps += flags.unroll_length * flags.batch_size
             acc.reduce_gradients(flags.batch_size)
             self.actor_since_learn = 0

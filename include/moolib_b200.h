@@ -161,7 +161,7 @@ typedef struct mb_ar_handle {
 #define MB_AR_ALGO_ONESHOT 1 /* every rank pulls all peers' buffers (P2P loads), lowest latency */
 #define MB_AR_ALGO_TWOSHOT 2 /* reduce-scatter by P2P loads + all-gather by P2P stores, 2(N-1)/N traffic */
 
-/* Allocate rank `rank`'s symmetric staging (nslots x 3 x max_bytes, cudaMalloc so it is IPC-exportable), barrier
+/* Allocate rank `rank`'s symmetric staging (nslots x 3 x max_bytes + one publish region, cudaMalloc so it is IPC-exportable), barrier
  * flags and the pinned result block on `device`.  world <= MB_AR_MAX_WORLD, 1 <= nslots <= MB_AR_MAX_SLOTS.
  * (replaces: src/accumulator.cc:847-874 allocateGradients -- pinned CPU staging) */
 MB_API int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int nslots, mb_ar_ctx** out);
@@ -230,6 +230,18 @@ MB_API int mb_ar_reduce_gated(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr,
  * wait for the slowest peer), reduce_us = K-A2 (the data movement).  MB_ESTATE if the round launched no kernel. */
 MB_API int mb_ar_round_times(mb_ar_ctx* ctx, int slot, float* gate_us, float* reduce_us);
 
+/* One-way bulk transfer of a tensor list between two members over NVLink (late-joiner model / buffer sync): the sender
+ * packs its tensors (flat layout of mb_ar_stage) into its PUBLISH region -- part of the symmetric block every peer has
+ * mapped --, tells the receiver over the host's control plane once its stream has passed the pack, and the receiver
+ * pulls the region into its own tensors with P2P loads.  No serialisation, no host staging, no socket payload.
+ * The host keeps the publisher from overwriting the region while a fetch is outstanding.
+ * (replaces: src/accumulator.cc:719-759, 810-836 -- parameters and buffers copied to the CPU, serialised and sent over the
+ *  RPC transport to every requesting peer) */
+MB_API int mb_ar_xfer_pack(mb_ar_ctx* ctx, const float* const* tensors, const uint64_t* numel, int ntensors,
+                           mb_stream_t stream);
+MB_API int mb_ar_xfer_unpack(mb_ar_ctx* ctx, int src_rank, float* const* tensors, const uint64_t* numel, int ntensors,
+                             mb_stream_t stream);
+
 /* Result of the most recent allreduce on `slot`: summed header and status (0 ok, MB_ETIMEOUT ...).  Reads pinned
  * host memory written by the kernel; only meaningful once the stream has reached the end of that allreduce
  * (query an event / synchronise first).  `status_out` may be NULL. */
@@ -241,6 +253,26 @@ MB_API uint64_t mb_ar_flat_numel(const uint64_t* numel, int ntensors);
 /* Host-side abort: makes every in-flight and future barrier wait on this context fail with MB_ETIMEOUT promptly
  * (peer death / regroup, SURVEY.md section 5 "Hook for HP-A").  Cleared by mb_ar_ctx_reset. */
 MB_API int mb_ar_abort(mb_ar_ctx* ctx);
+
+/* =====================================================================================================
+ * Learner-side steps next to the hot paths (launch-bound chains of tiny ops in the reference's example)
+ * ===================================================================================================== */
+
+/* K-L1  V-trace from log importance weights, [T, B] fp32 contiguous inputs, bootstrap_value [B]:
+ *   rho = exp(log_rho); c = min(rho, 1); delta = min(rho, clip_rho) * (r + d * V_{t+1} - V_t)
+ *   acc_t = delta_t + d_t * c_t * acc_{t+1};  vs_t = acc_t + V_t
+ *   pg_adv_t = min(rho, clip_pg_rho) * (r_t + d_t * vs_{t+1} - V_t)
+ * in the reference's operation order, every fp32 rounding kept.  has_clip_* == 0 disables that clamp (None).
+ * (replaces: examples/common/vtrace.py:207-242 from_importance_weights -- ~100 kernel launches for T = 20) */
+MB_API int mb_vtrace_f32(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
+                         const float* bootstrap_value, int has_clip_rho, float clip_rho, int has_clip_pg_rho,
+                         float clip_pg_rho, uint64_t T, uint64_t B, float* vs_out, float* pg_advantages_out,
+                         mb_stream_t stream);
+
+/* K-L2  dst[i] = (float)src[i] * scale  (scale = 1.0f/255.0f: the observation normalisation; ATen evaluates
+ * `x.float() / 255.0` as a multiplication by the fp32 reciprocal, so the results are bit-identical).
+ * (replaces: examples/atari/models.py:94 -- two elementwise passes) */
+MB_API int mb_u8_to_f32(const uint8_t* src, float* dst, uint64_t n, float scale, mb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ except ImportError as e:  # pragma: no cover
         "moolib_b200._C (the compiled host layer) is missing or failed to load; build it with "
         "`python moolib_b200/build.py`") from e
 
-from ._C import Batcher, UnrollBatcher, to_device  # noqa: E402,F401
+from ._C import Batcher, UnrollBatcher, to_device, u8_to_float, vtrace_from_importance_weights  # noqa: E402,F401
 
 for _name in ("Accumulator", "Group", "Rpc", "Broker", "EnvPool", "EnvStepper", "EnvStepperFuture", "Future",
               "AllReduce", "create_uid", "set_log_level", "set_logging", "set_max_threads"):

@@ -17,7 +17,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmoolib_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CUDA_SOURCES = ["mb_core.cu", "mb_copy.cu", "mb_allreduce.cu"]
+CUDA_SOURCES = ["mb_core.cu", "mb_copy.cu", "mb_allreduce.cu", "mb_learner.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",

@@ -73,5 +73,6 @@ void bind_batcher(py::module_& m);
 void bind_accumulator(py::module_& m);
 void bind_envpool(py::module_& m);
 void bind_rpc(py::module_& m);
+void bind_learner_ops(py::module_& m);
 
 }  // namespace mbh

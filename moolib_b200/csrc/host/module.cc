@@ -9,4 +9,5 @@ PYBIND11_MODULE(_C, m) {
   mbh::bind_rpc(m);
   mbh::bind_accumulator(m);
   mbh::bind_envpool(m);
+  mbh::bind_learner_ops(m);
 }

@@ -80,6 +80,7 @@ struct HandleImpl {
   uint64_t block_ptr;     // owner's virtual address of the block (same-process peers use it directly)
   uint64_t base_offset;   // block_ptr - base of the driver allocation that the IPC handle maps
   uint64_t sync_offset;   // SyncBlock offset inside the block
+  uint64_t xfer_offset;   // publish region offset inside the block
   uint64_t max_bytes;
   int32_t nslots;
   int32_t ipc_ok;
@@ -109,6 +110,7 @@ struct mb_ar_ctx {
   void* block = nullptr;             // the one IPC-exported allocation: [staging | SyncBlock], multiple of 2 MiB
   uint64_t block_bytes = 0, sync_offset = 0;
   float* staging = nullptr;          // nslots * MB_AR_BUFS_PER_SLOT buffers (ring, see mb_ar_allreduce)
+  uint64_t xfer_offset = 0;          // the publish region (max_bytes) behind the ring: mb_ar_xfer_pack / _unpack
   mb::SyncBlock* sync = nullptr;
   void* peer_block[MB_AR_MAX_WORLD] = {};  // IPC-opened base of each peer's block (what must be closed)
   float* peer_staging[MB_AR_MAX_WORLD] = {};
@@ -274,6 +276,38 @@ __global__ void __launch_bounds__(kArThreads) ar_stage_kernel(const __grid_const
       g = make_float4(__fadd_rn(a.x, g.x), __fadd_rn(a.y, g.y), __fadd_rn(a.z, g.z), __fadd_rn(a.w, g.w));
     }
     *d = g;
+  }
+}
+
+// ---- publish region: one-way bulk transfer of a tensor list between members (late-joiner model sync) -------------
+
+struct UnpackParams {
+  const float* src;  // the source rank's publish region (peer memory)
+  const TensorEnt* tab;
+  uint32_t ntensors;
+  uint64_t total_vec;
+};
+
+// dst tensors <- flat layout in `src`, 4 x 16 B peer loads in flight per thread
+__global__ void __launch_bounds__(kArThreads) ar_unpack_kernel(const __grid_constant__ UnpackParams p) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  const TensorTable tb = load_table(dyn_smem, p.tab, p.ntensors);
+  __syncthreads();
+  const uint64_t per_block = (p.total_vec + gridDim.x - 1) / gridDim.x;
+  const uint64_t begin = (uint64_t)blockIdx.x * per_block;
+  const uint64_t end = min(begin + per_block, p.total_vec);
+  uint32_t cur = 0;
+  for (uint64_t base = begin; base < end; base += 4ull * kArThreads) {
+    float4 x[4];
+    uint64_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = base + (uint64_t)k * kArThreads + threadIdx.x;
+      if (v[k] < end) x[k] = ld_peer_f4(p.src + v[k] * 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (v[k] < end) scatter_vec(tb, v[k], x[k], cur);
   }
 }
 
@@ -936,7 +970,8 @@ int mb_ar_ctx_create(int rank, int world, int device, uint64_t max_bytes, int ns
     cudaError_t e__ = (expr);                                                         \
     if (e__ != cudaSuccess) return fail(cuda_fail(e__, #expr, __FILE__, __LINE__));   \
   } while (0)
-  const uint64_t staging_bytes = (ctx->max_bytes * kBufs * (uint64_t)nslots + 255) & ~255ull;
+  ctx->xfer_offset = (ctx->max_bytes * kBufs * (uint64_t)nslots + 255) & ~255ull;
+  const uint64_t staging_bytes = (ctx->xfer_offset + ctx->max_bytes + 255) & ~255ull;
   ctx->sync_offset = staging_bytes;
   ctx->block_bytes = (staging_bytes + sizeof(SyncBlock) + (2ull << 20) - 1) & ~((2ull << 20) - 1);
   MB_TRY(cudaMalloc(&ctx->block, ctx->block_bytes));
@@ -1007,6 +1042,7 @@ int mb_ar_ctx_export(mb_ar_ctx* ctx, mb_ar_handle* out) {
   h.rank = ctx->rank;
   h.block_ptr = reinterpret_cast<uint64_t>(ctx->block);
   h.sync_offset = ctx->sync_offset;
+  h.xfer_offset = ctx->xfer_offset;
   h.max_bytes = ctx->max_bytes;
   h.nslots = ctx->nslots;
   h.ipc_ok = 1;
@@ -1207,6 +1243,71 @@ int mb_ar_round_times(mb_ar_ctx* ctx, int slot, float* gate_us, float* reduce_us
   if (gate_us) *gate_us = a * 1e3f;
   if (reduce_us) *reduce_us = b * 1e3f;
   return MB_OK;
+}
+
+int mb_ar_xfer_pack(mb_ar_ctx* ctx, const float* const* tensors, const uint64_t* numel, int ntensors, mb_stream_t stream_) {
+  MB_CHECK_ARG(ctx && tensors && numel, "mb_ar_xfer_pack: null argument");
+  MB_CHECK_ARG(ntensors >= 1 && ntensors <= kArMaxTensors, "mb_ar_xfer_pack: ntensors %d not in [1,%d]", ntensors, kArMaxTensors);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint64_t total = 0;
+  int rc = sync_table(ctx, 0, reinterpret_cast<const void* const*>(tensors), numel, ntensors, &total, stream);
+  if (rc) return rc;
+  MB_CHECK_ARG(total * 4 <= ctx->max_bytes, "mb_ar_xfer_pack: %llu bytes exceed the context's max_bytes %llu",
+               (unsigned long long)(total * 4), (unsigned long long)ctx->max_bytes);
+  if (total == 0) return 0;
+  StageParams p;
+  p.staging = reinterpret_cast<float*>(static_cast<char*>(ctx->block) + ctx->xfer_offset);
+  p.tab = ctx->tab_dev[0];
+  p.ntensors = (uint32_t)ntensors;
+  p.accumulate = 0;
+  p.zero_src = 0;
+  p.total_vec = total / 4;
+  const int sms = sm_count(ctx->device);
+  if (sms <= 0) return MB_ECUDA;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((p.total_vec + kArThreads - 1) / kArThreads, (uint64_t)sms * 4);
+  const size_t smem = table_bytes(p.ntensors);
+  rc = ensure_dyn_smem(reinterpret_cast<const void*>(ar_stage_kernel), smem);
+  if (rc) return rc;
+  ar_stage_kernel<<<grid, kArThreads, smem, stream>>>(p);
+  MB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int mb_ar_xfer_unpack(mb_ar_ctx* ctx, int src_rank, float* const* tensors, const uint64_t* numel, int ntensors,
+                      mb_stream_t stream_) {
+  MB_CHECK_ARG(ctx && tensors && numel, "mb_ar_xfer_unpack: null argument");
+  MB_CHECK_ARG(ntensors >= 1 && ntensors <= kArMaxTensors, "mb_ar_xfer_unpack: ntensors %d not in [1,%d]", ntensors, kArMaxTensors);
+  MB_CHECK_ARG(src_rank >= 0 && src_rank < ctx->world, "mb_ar_xfer_unpack: source rank %d not in [0,%d)", src_rank, ctx->world);
+  std::lock_guard<std::mutex> l(ctx->mu);
+  if (!ctx->imported[src_rank]) {
+    set_error("mb_ar_xfer_unpack: peer %d has not been imported", src_rank);
+    return MB_ESTATE;
+  }
+  DeviceGuard g(ctx->device);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  uint64_t total = 0;
+  int rc = sync_table(ctx, 1, reinterpret_cast<const void* const*>(tensors), numel, ntensors, &total, stream);
+  if (rc) return rc;
+  MB_CHECK_ARG(total * 4 <= ctx->max_bytes, "mb_ar_xfer_unpack: %llu bytes exceed the context's max_bytes %llu",
+               (unsigned long long)(total * 4), (unsigned long long)ctx->max_bytes);
+  if (total == 0) return 0;
+  UnpackParams p;
+  // peer_staging[r] is the base of rank r's block (the ring starts there); the publish region sits at xfer_offset
+  p.src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(ctx->peer_staging[src_rank]) + ctx->xfer_offset);
+  p.tab = ctx->tab_dev[1];
+  p.ntensors = (uint32_t)ntensors;
+  p.total_vec = total / 4;
+  const int sms = sm_count(ctx->device);
+  if (sms <= 0) return MB_ECUDA;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((p.total_vec + 4ull * kArThreads - 1) / (4ull * kArThreads), (uint64_t)sms * 2);
+  const size_t smem = table_bytes(p.ntensors);
+  rc = ensure_dyn_smem(reinterpret_cast<const void*>(ar_unpack_kernel), smem);
+  if (rc) return rc;
+  ar_unpack_kernel<<<std::max<uint32_t>(grid, 1), kArThreads, smem, stream>>>(p);
+  MB_CUDA(cudaGetLastError());
+  return 1;
 }
 
 int mb_ar_result(mb_ar_ctx* ctx, int slot, mb_ar_hdr* sum_out, int* status_out) {

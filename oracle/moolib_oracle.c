@@ -10,6 +10,7 @@
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off: no FMA contraction, IEEE fp32 adds/multiplies).
  */
+#include <math.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -186,5 +187,58 @@ int oracle_allreduce_rankorder(const float* const* in, const oracle_hdr* hdr, in
     out[i] = do_scale ? acc * s : acc;
   }
   if (out_hdr) *out_hdr = tot;
+  return 0;
+}
+
+/* ---- learner-side steps next to the hot paths ------------------------------------------ */
+
+static float oracle_clamp_max(float x, float c, int on) {
+  if (!on || x != x) return x; /* torch.clamp propagates NaN */
+  return x < c ? x : c;
+}
+
+/* V-trace from log importance weights: examples/common/vtrace.py:207-242 from_importance_weights, [T, B] fp32.
+ *   rhos = exp(log_rhos); clipped_rhos = clamp(rhos, max=clip_rho); cs = clamp(rhos, max=1)            (:207-213)
+ *   deltas = clipped_rhos * (rewards + discounts * values_t_plus_1 - values)                              (:215-219)
+ *   acc = deltas[t] + discounts[t] * cs[t] * acc   for t = T-1 .. 0;   vs = acc + values                  (:221-230)
+ *   pg_advantages = clamp(rhos, max=clip_pg_rho) * (rewards + discounts * vs_t_plus_1 - values)            (:233-239)
+ * Every operation rounds to fp32 on its own (compile with -ffp-contract=off).  expf is the C library's: it may differ
+ * from the device's expf in the last bit, which is why parity with this function is checked at 1e-6 relative while
+ * parity with the PyTorch restatement on the same device is bit-exact. */
+int oracle_vtrace(const float* log_rhos, const float* discounts, const float* rewards, const float* values,
+                  const float* bootstrap, int has_clip_rho, float clip_rho, int has_clip_pg_rho, float clip_pg_rho,
+                  size_t T, size_t B, float* vs_out, float* pg_out) {
+  for (size_t j = 0; j < B; ++j) {
+    float acc = 0.0f, v_next = bootstrap[j], vs_next = bootstrap[j];
+    for (size_t t = T; t-- > 0;) {
+      const size_t i = t * B + j;
+      const float rho = expf(log_rhos[i]);
+      const float d = discounts[i], r = rewards[i], v = values[i];
+      const float crho = oracle_clamp_max(rho, clip_rho, has_clip_rho);
+      const float c = oracle_clamp_max(rho, 1.0f, 1);
+      float tmp = d * v_next;
+      tmp = r + tmp;
+      tmp = tmp - v;
+      const float delta = crho * tmp;
+      float dc = d * c;
+      dc = dc * acc;
+      acc = delta + dc;
+      const float vs = acc + v;
+      float q = d * vs_next;
+      q = r + q;
+      q = q - v;
+      pg_out[i] = oracle_clamp_max(rho, clip_pg_rho, has_clip_pg_rho) * q;
+      vs_out[i] = vs;
+      v_next = v;
+      vs_next = vs;
+    }
+  }
+  return 0;
+}
+
+/* x.float() / 255.0 as ATen evaluates it on CUDA: fp32 multiplication by the fp32 reciprocal of the scalar
+ * (examples/atari/models.py:94; aten/src/ATen/native/cuda/BinaryDivTrueKernel.cu: `inv_b = 1 / b`, `a * inv_b`). */
+int oracle_u8_to_f32(const uint8_t* src, float* dst, size_t n, float scale) {
+  for (size_t i = 0; i < n; ++i) dst[i] = (float)src[i] * scale;
   return 0;
 }

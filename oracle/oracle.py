@@ -21,7 +21,7 @@ REF_DIR = os.path.join(_HERE, "_ref")
 __all__ = [
     "build", "lib", "stack_slot", "cat_narrow", "copy2d", "fill_batch", "scatter_actions", "stage",
     "allreduce_tree", "allreduce_rankorder", "flat_layout", "OracleBatcher", "load_reference", "reference_available",
-    "allreduce_tolerance",
+    "allreduce_tolerance", "vtrace", "u8_to_f32",
 ]
 
 
@@ -154,6 +154,30 @@ def allreduce_tolerance(inputs, reference_out, scale_factor=1.0):
         if a is not None:
             s += np.abs(a.astype(np.float64))
     return 1e-6 * np.maximum(np.abs(reference_out.astype(np.float64)), s * scale_factor)
+
+
+def vtrace(log_rhos, discounts, rewards, values, bootstrap_value, clip_rho=1.0, clip_pg_rho=1.0):
+    """examples/common/vtrace.py:156-242 from_importance_weights on [T, B] float32 arrays -> (vs, pg_advantages)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (log_rhos, discounts, rewards, values, bootstrap_value)]
+    T = arrs[0].shape[0]
+    B = arrs[0].size // max(T, 1)
+    vs, pg = np.empty_like(arrs[0]), np.empty_like(arrs[0])
+    f = lib().oracle_vtrace
+    f.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_size_t,
+                                          ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    f(*[_u8(a) for a in arrs], int(clip_rho is not None), float(clip_rho or 0.0), int(clip_pg_rho is not None),
+      float(clip_pg_rho or 0.0), T, B, _u8(vs), _u8(pg))
+    return vs, pg
+
+
+def u8_to_f32(src, scale=np.float32(1.0) / np.float32(255.0)):
+    """examples/atari/models.py:94 `x.float() / 255.0` as ATen evaluates it: x * fp32(1/255)."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    out = np.empty(src.shape, dtype=np.float32)
+    f = lib().oracle_u8_to_f32
+    f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float]
+    f(_u8(src), _u8(out), src.size, float(scale))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -273,8 +273,37 @@ def make_envpool():
     print("envpool:", steps, "steps of", bs, "envs")
 
 
+def make_vtrace():
+    """The reference's own V-trace (examples/common/vtrace.py, pure PyTorch, imported from the reference tree) and its
+    observation normalisation `x.float() / 255.0` (examples/atari/models.py:94) on seeded inputs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_vtrace", "/root/reference/examples/common/vtrace.py")
+    ref_vtrace = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_vtrace)
+    out, cases = {}, []
+    for ci, (T, B, clip, clip_pg) in enumerate([(20, 32, 1.0, 1.0), (5, 7, 1.0, 1.0), (1, 3, 1.0, 1.0), (20, 64, 0.8, 2.0),
+                                                (11, 130, None, None)]):
+        lr = gen_input(8000 + 10 * ci, [T, B], "f32") * 0.5
+        disc = (gen_input(8001 + 10 * ci, [T, B], "bool") | gen_input(8002 + 10 * ci, [T, B], "bool")).astype(np.float32) * 0.99
+        rew = gen_input(8003 + 10 * ci, [T, B], "f32")
+        val = gen_input(8004 + 10 * ci, [T, B], "f32")
+        boot = gen_input(8005 + 10 * ci, [B], "f32")
+        r = ref_vtrace.from_importance_weights(torch.from_numpy(lr), torch.from_numpy(disc), torch.from_numpy(rew),
+                                               torch.from_numpy(val), torch.from_numpy(boot), clip, clip_pg)
+        out[f"c{ci}_vs"] = r.vs.numpy().copy()
+        out[f"c{ci}_pg"] = r.pg_advantages.numpy().copy()
+        cases.append(repr((T, B, clip, clip_pg)))
+    x = gen_input(8900, [3, 5, 4, 8, 8], "u8")
+    out["norm_in_seed"] = np.array(8900)
+    out["norm_out"] = (torch.from_numpy(x).float() / 255.0).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "vtrace_golden.npz"), cases=np.array(cases), **out)
+    print("vtrace:", len(cases), "cases")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["batcher", "allreduce", "accumulator", "envpool"]
+    which = sys.argv[1:] or ["batcher", "allreduce", "accumulator", "envpool", "vtrace"]
+    if "vtrace" in which:
+        make_vtrace()
     if "batcher" in which:
         make_batcher()
     if "allreduce" in which:
