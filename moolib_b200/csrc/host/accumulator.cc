@@ -23,6 +23,8 @@
 #include "device_reduce.h"
 
 #include <ATen/ATen.h>
+
+#include <set>
 #include <cuda_runtime_api.h>
 
 namespace mbh {
@@ -160,7 +162,7 @@ class Accumulator {
     }
     if (arStream_) cudaStreamDestroy(arStream_);
     unhandleAll(*parts_.rpc, {"Acc::requestModel/" + resName_, "Acc::modelUpdate/" + resName_,
-                              "Acc::buffersUpdate/" + resName_});
+                              "Acc::buffersUpdate/" + resName_, "Acc::modelFetched/" + resName_});
   }
 
   void connect(const std::string& address) { parts_.rpc->connect(address); }
@@ -384,7 +386,9 @@ class Accumulator {
   std::shared_ptr<DeviceReducer> reducer() {
     if (!reducer_) {
       auto gs = ensureGrads();
-      reducer_ = parts_.reducers->get("acc/" + resName_, device_, std::max<uint64_t>(flatBytes(gs), 16), (int)slots_.size());
+      // big enough for the gradient set AND for the publish region that carries parameters + buffers to late joiners
+      reducer_ = parts_.reducers->get("acc/" + resName_, device_, std::max<uint64_t>({flatBytes(gs), modelFlatBytes(), 16}),
+                                      (int)slots_.size());
     }
     return reducer_;
   }
@@ -672,15 +676,27 @@ class Accumulator {
       Reader r(p);
       uint32_t syncId = r.u32();
       std::string peer = r.str();
+      const bool viaNvlink = !r.done() && r.u32() != 0;  // the requester has this leader's publish region mapped
       std::lock_guard<std::mutex> l(netMu_);
       if (syncId != netSyncId_) return;
       if (std::find(requestedModelUpdate_.begin(), requestedModelUpdate_.end(), peer) == requestedModelUpdate_.end())
         requestedModelUpdate_.push_back(peer);
+      if (viaNvlink) requestedViaNvlink_.insert(peer);
+      else requestedViaNvlink_.erase(peer);
+    });
+    parts_.rpc->handle("Acc::modelFetched/" + resName_, [this](const std::string&, const Bytes& p) {
+      Reader r(p);
+      uint32_t syncId = r.u32();
+      std::string peer = r.str();
+      std::lock_guard<std::mutex> l(netMu_);
+      if (syncId == netSyncId_) publishPending_.erase(peer);
     });
     parts_.rpc->handle("Acc::modelUpdate/" + resName_, [this](const std::string&, const Bytes& p) {
       Reader r(p);
       uint32_t syncId = r.u32();
-      bool regular = r.u32() != 0;
+      const uint32_t kind = r.u32();
+      const bool regular = (kind & 1u) != 0;
+      const bool viaNvlink = (kind & 2u) != 0;  // float CUDA tensors wait in the sender's publish region
       int64_t version = r.i64();
       uint32_t np = r.u32();
       std::vector<Bytes> ps(np);
@@ -697,6 +713,7 @@ class Accumulator {
       newBuffers_ = std::move(bs);
       newUserState_ = std::move(state);
       newModelVersion_ = version;
+      newViaNvlink_ = viaNvlink;
       haveNewParameters_ = true;
     });
     parts_.rpc->handle("Acc::buffersUpdate/" + resName_, [this](const std::string&, const Bytes& p) {
@@ -719,19 +736,59 @@ class Accumulator {
     Writer w;
     w.u32(hSyncId_);
     w.str(myName_);
+    // NVLink model sync: possible once this peer's context is connected for the epoch, i.e. the leader's
+    // publish region is mapped here
+    w.u32(nvlinkSyncPossible() ? 1 : 0);
     parts_.rpc->send(syncLeader_, "Acc::requestModel/" + resName_, w.b);
   }
 
-  Bytes packModel(bool regular, const Bytes& state) {
+  bool nvlinkSyncPossible() {
+    return gradsOnCuda_ && reducerReady_ && reducer_ && reducer_->syncId() == hSyncId_ && reducer_->world() > 1 && !nvlinkOff_;
+  }
+  // tensors that travel through the publish region: float32, on the accumulator's device (same predicate on both sides)
+  bool viaPublishRegion(const torch::Tensor& t) const {
+    return t.is_cuda() && t.get_device() == device_ && t.scalar_type() == torch::kFloat32 && t.numel() > 0;
+  }
+  uint64_t modelFlatBytes() {
+    std::vector<uint64_t> n;
+    for (auto* list : {&params_, &buffers_})
+      for (auto& t : *list)
+        if (viaPublishRegion(t)) n.push_back((uint64_t)t.numel());
+    return n.empty() ? 0 : mb_ar_flat_numel(n.data(), (int)n.size()) * 4;
+  }
+
+  // kind bit 0: regular (periodic) update, bit 1: float CUDA tensors are published over NVLink instead of serialised
+  Bytes packModel(bool regular, const Bytes& state, bool viaNvlink = false) {
     torch::NoGradGuard ng;
     Writer w;
     w.u32(hSyncId_);
-    w.u32(regular ? 1 : 0);
+    w.u32((regular ? 1u : 0u) | (viaNvlink ? 2u : 0u));
     w.i64(modelVersion_);
+    if (viaNvlink) {
+      // parameters + buffers -> this rank's publish region, ONE pack launch; the message below only goes out once
+      // the stream has passed it (reference: every tensor .to(cpu), serialised, sent over the RPC transport)
+      std::vector<const float*> ptrs;
+      std::vector<uint64_t> numel;
+      std::vector<torch::Tensor> keep;
+      for (auto* list : {&params_, &buffers_})
+        for (auto& t : *list)
+          if (viaPublishRegion(t)) {
+            keep.push_back(t.detach().contiguous());
+            ptrs.push_back(keep.back().data_ptr<float>());
+            numel.push_back((uint64_t)keep.back().numel());
+          }
+      c10::cuda::CUDAGuard dg(device_);
+      if (!ptrs.empty())
+        launch_counter() += check(mb_ar_xfer_pack(reducer()->ctx(), ptrs.data(), numel.data(), (int)ptrs.size(),
+                                                  current_stream(device_)),
+                                  "Accumulator model publish");
+      cudaStreamSynchronize(c10::cuda::getCurrentCUDAStream(device_).stream());
+      ++nvlinkPublishes_;
+    }
     w.u32((uint32_t)params_.size());
-    for (auto& p : params_) w.str(packTensor(p.detach().to(torch::kCPU)));
+    for (auto& p : params_) w.str(viaNvlink && viaPublishRegion(p) ? Bytes() : packTensor(p.detach().to(torch::kCPU)));
     w.u32((uint32_t)buffers_.size());
-    for (auto& b : buffers_) w.str(packTensor(b.detach().to(torch::kCPU)));
+    for (auto& b : buffers_) w.str(viaNvlink && viaPublishRegion(b) ? Bytes() : packTensor(b.detach().to(torch::kCPU)));
     w.str(state);
     return w.b;
   }
@@ -749,13 +806,37 @@ class Accumulator {
       std::lock_guard<std::mutex> nl(netMu_);
       requested.swap(requestedModelUpdate_);
     }
-    Bytes msg;
-    for (auto& n : requested) {
-      if (n != myName_ && std::find(members_.begin(), members_.end(), n) != members_.end()) {
-        if (msg.empty()) msg = packModel(false, pickled);
-        parts_.rpc->send(n, "Acc::modelUpdate/" + resName_, msg);
+    // recipients that can pull over NVLink get the publish-region variant (packed once for all of them); the region is
+    // not overwritten while a previous fetch is unacknowledged (10 s grace), such requests wait for a later tick
+    std::vector<std::string> viaTcp, viaNvl, later;
+    {
+      std::lock_guard<std::mutex> nl(netMu_);
+      if (!publishPending_.empty() && now - publishSince_ >= std::chrono::seconds(10)) publishPending_.clear();
+      for (auto& n : requested) {
+        if (n == myName_ || std::find(members_.begin(), members_.end(), n) == members_.end()) continue;
+        if (requestedViaNvlink_.count(n) && nvlinkSyncPossible()) {
+          if (publishPending_.empty()) viaNvl.push_back(n);
+          else later.push_back(n);
+        } else {
+          viaTcp.push_back(n);
+        }
       }
+      for (auto& n : later) requestedModelUpdate_.push_back(n);
+      for (auto& n : viaNvl) {
+        publishPending_.insert(n);
+        requestedViaNvlink_.erase(n);
+      }
+      if (!viaNvl.empty()) publishSince_ = now;
     }
+    if (!viaTcp.empty()) {
+      Bytes msg = packModel(false, pickled);
+      for (auto& n : viaTcp) parts_.rpc->send(n, "Acc::modelUpdate/" + resName_, msg);
+    }
+    if (!viaNvl.empty()) {
+      Bytes msg = packModel(false, pickled, /*viaNvlink=*/true);
+      for (auto& n : viaNvl) parts_.rpc->send(n, "Acc::modelUpdate/" + resName_, msg);
+    }
+    if (!later.empty()) wantsUserState_ = true;
     if (syncLeader_ == myName_ && now - lastSentModel_ >= std::chrono::seconds(600)) {
       lastSentModel_ = now;
       Bytes reg = packModel(true, pickled);
@@ -801,20 +882,56 @@ class Accumulator {
     torch::NoGradGuard ng;
     std::vector<Bytes> ps, bs;
     Bytes state;
+    bool viaNvlink = false;
     {
       std::lock_guard<std::mutex> nl(netMu_);
       haveNewParameters_ = false;
       haveNewBuffers_ = false;
       modelVersion_ = newModelVersion_;
+      viaNvlink = newViaNvlink_;
       ps.swap(newParameters_);
       bs.swap(newBuffers_);
       state.swap(newUserState_);
     }
     lastReceivedModel_ = Clock::now();
     if (ps.size() != params_.size()) throw std::runtime_error("Model parameters size mismatch in update!");
-    if (bs.size() != buffers_.size()) throw std::runtime_error("Model parameters size mismatch in update!");
-    for (size_t i = 0; i < params_.size(); ++i) params_[i].copy_(unpackTensor(ps[i]).view_as(params_[i]), true);
-    for (size_t i = 0; i < buffers_.size(); ++i) buffers_[i].copy_(unpackTensor(bs[i]).view_as(buffers_[i]), true);
+    if (bs.size() != buffers_.size()) throw std::runtime_error("Model buffers size mismatch in update!");
+    if (viaNvlink) {
+      // pull the leader's publish region straight into the parameter / buffer tensors: ONE launch of P2P loads
+      if (!nvlinkSyncPossible()) throw std::runtime_error("moolib_b200: NVLink model update without a connected context");
+      auto it = std::find(members_.begin(), members_.end(), syncLeader_);
+      if (it == members_.end()) throw std::runtime_error("moolib_b200: model update from a leader outside the group");
+      std::vector<float*> ptrs;
+      std::vector<uint64_t> numel;
+      std::vector<std::pair<torch::Tensor, torch::Tensor>> fixups;  // (destination, contiguous temporary)
+      for (auto* list : {&params_, &buffers_})
+        for (auto& t : *list)
+          if (viaPublishRegion(t)) {
+            torch::Tensor d = t.detach();
+            if (!d.is_contiguous()) {
+              fixups.emplace_back(d, torch::empty_like(d, d.options().memory_format(c10::MemoryFormat::Contiguous)));
+              d = fixups.back().second;
+            }
+            ptrs.push_back(d.data_ptr<float>());
+            numel.push_back((uint64_t)d.numel());
+          }
+      c10::cuda::CUDAGuard dg(device_);
+      if (!ptrs.empty())
+        launch_counter() += check(mb_ar_xfer_unpack(reducer()->ctx(), (int)(it - members_.begin()), ptrs.data(), numel.data(),
+                                                    (int)ptrs.size(), current_stream(device_)),
+                                  "Accumulator model fetch");
+      for (auto& f : fixups) f.first.copy_(f.second);
+      cudaStreamSynchronize(c10::cuda::getCurrentCUDAStream(device_).stream());
+      ++nvlinkFetches_;
+      Writer ack;
+      ack.u32(hSyncId_);
+      ack.str(myName_);
+      parts_.rpc->send(syncLeader_, "Acc::modelFetched/" + resName_, ack.b);  // the leader may reuse its region
+    }
+    for (size_t i = 0; i < params_.size(); ++i)
+      if (!(viaNvlink && viaPublishRegion(params_[i]))) params_[i].copy_(unpackTensor(ps[i]).view_as(params_[i]), true);
+    for (size_t i = 0; i < buffers_.size(); ++i)
+      if (!(viaNvlink && viaPublishRegion(buffers_[i]))) buffers_[i].copy_(unpackTensor(bs[i]).view_as(buffers_[i]), true);
     userState_ = pickleLoads(state);
     hasNewUserState_ = true;
     hasReceivedModel_ = true;
@@ -860,8 +977,19 @@ class Accumulator {
           std::lock_guard<std::mutex> gl(parts_.info->mutex);
           members_ = parts_.info->members;
         }
-        if (version != modelVersion_ || !hasReceivedModel_) requestModel();
-        else lastReceivedModel_ = now;
+        if (version != modelVersion_ || !hasReceivedModel_) {
+          // CUDA models: wait (up to 2 s) for the NVLink context of this epoch, then the model comes over NVLink
+          if (gradsOnCuda_ && !nvlinkOff_ && !reducerReady_ && syncLeader_ != myName_) {
+            isWaitingForModel_ = true;
+            isWaitingForModelTimestamp_ = now;
+            deferredRequestSince_ = now;
+            requestDeferred_ = true;
+          } else {
+            requestModel();
+          }
+        } else {
+          lastReceivedModel_ = now;
+        }
       } else if (hSyncId_ == parts_.info->syncId.load()) {
         resync();
       }
@@ -878,6 +1006,10 @@ class Accumulator {
         repointForAccumulation();
       }
     }
+    if (requestDeferred_ && (reducerReady_ || now - deferredRequestSince_ >= std::chrono::seconds(2))) {
+      requestDeferred_ = false;
+      if (hSyncId_ != 0 && !syncLeader_.empty()) requestModel();
+    }
     MBH_PHASE("update:checkGradientResult");
     checkGradientResult();
     MBH_PHASE("update:after-check");
@@ -893,12 +1025,15 @@ class Accumulator {
         std::lock_guard<std::mutex> nl(netMu_);
         netSyncId_ = hSyncId_;
         requestedModelUpdate_.clear();
+        requestedViaNvlink_.clear();
+        publishPending_.clear();
         haveNewParameters_ = false;
       }
       hasNewUserState_ = false;
       wantsUserState_ = false;
       isFindingLeader_ = true;
       isWaitingForModel_ = false;
+      requestDeferred_ = false;
       hasGradients_ = false;
       reducerReady_ = false;
       members_.clear();
@@ -973,6 +1108,8 @@ class Accumulator {
     d["reducer_sync"] = reducer_ ? reducer_->syncId() : 0u;
     d["model_version"] = modelVersion_;
     d["last_error"] = lastError_;
+    d["nvlink_model_publishes"] = nvlinkPublishes_;
+    d["nvlink_model_fetches"] = nvlinkFetches_;
     d["next_index"] = nextIndex_;
     auto& v = slots_[nextResultIndex_];
     if (v) {
@@ -1064,6 +1201,13 @@ class Accumulator {
   std::shared_ptr<DeviceReducer> reducer_;
   bool reducerReady_ = false;
   cudaStream_t arStream_ = nullptr;
+  bool nvlinkOff_ = [] {
+    const char* e = std::getenv("MOOLIB_B200_NVLINK_MODEL_SYNC");
+    return e && *e == '0';
+  }();
+  bool requestDeferred_ = false;
+  Clock::time_point deferredRequestSince_{};
+  uint64_t nvlinkPublishes_ = 0, nvlinkFetches_ = 0;
   std::unique_ptr<GradArena> arena_;
   int appliedSlot_ = -1;  // slot whose result buffer .grad currently shows (-1: none)
   struct RoundTiming {
@@ -1098,6 +1242,10 @@ class Accumulator {
   int64_t netModelVersion_ = 0;
   bool netWaitingForModel_ = false;
   std::vector<std::string> requestedModelUpdate_;
+  std::set<std::string> requestedViaNvlink_;  // requesters that can pull from this peer's publish region
+  std::set<std::string> publishPending_;      // NVLink recipients that have not acknowledged their fetch yet
+  Clock::time_point publishSince_{};
+  bool newViaNvlink_ = false;
   bool haveNewParameters_ = false, haveNewBuffers_ = false;
   int64_t newModelVersion_ = 0;
   std::vector<Bytes> newParameters_, newBuffers_;

@@ -148,8 +148,10 @@ if rank == 0:
     broker = moolib.Broker(); broker.listen(addr)
 rpc = moolib.Rpc(); rpc.set_name(f'peer{rank}'); rpc.set_timeout(30); rpc.connect(addr)
 group = moolib.Group(rpc, 'g'); group.set_sort_order(rank)
-torch.manual_seed(0)
+torch.manual_seed(1000 + rank)   # every peer starts from DIFFERENT weights: the elected leader's must win
 m = torch.nn.Linear(32, 31).cuda()
+m.register_buffer('running', torch.full((5,), float(rank), device='cuda'))
+m.register_buffer('steps', torch.tensor([rank], dtype=torch.int64, device='cuda'))   # non-float buffer: control plane
 acc = moolib.Accumulator('acc', m.parameters(), m.buffers(), group=group)
 acc.set_virtual_batch_size(10 * world)
 def pump():
@@ -160,6 +162,15 @@ def pump():
 t0 = time.time()
 while not (acc.connected() and len(group.members()) == world):
     pump(); time.sleep(0.001); assert time.time() - t0 < 90, group.members()
+# late-joiner model sync (SURVEY 8(f)-3): parameters + float buffers came out of the leader's publish region over NVLink
+import zlib
+ds = acc.debug_state()
+crc = zlib.crc32(torch.cat([p.detach().flatten() for p in m.parameters()] + [m.running]).cpu().numpy().tobytes())
+print(f'PARAMCRC {rank} {crc:08x} {int(m.steps.item())}', flush=True)
+if acc.is_leader():
+    assert ds['nvlink_model_publishes'] >= 1, ds
+else:
+    assert ds['nvlink_model_fetches'] >= 1, ds
 # group.all_reduce on CUDA tensors (A8)
 x = torch.from_numpy(gen_input(900 + rank, [64, 64], 'f32')).cuda()
 f = group.all_reduce('t', x)
@@ -261,3 +272,5 @@ def test_accumulator_across_processes(world, tmp_path):
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") == world
+    crcs = {tuple(ln.split()[2:]) for ln in r.stdout.splitlines() if ln.startswith("PARAMCRC")}
+    assert len(crcs) == 1, f"peers hold different models after the NVLink model sync: {crcs}"
