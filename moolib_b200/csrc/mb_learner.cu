@@ -36,25 +36,84 @@ struct VtraceParams {
   int has_clip_rho, has_clip_pg_rho;
 };
 
-__global__ void __launch_bounds__(128) vtrace_kernel(const VtraceParams p) {
+constexpr int kVtCols = 32;      // batch columns per block
+constexpr int kVtThreads = 128;
+
+// A block owns kVtCols columns.  All threads first pull the four [T, cols] input panels into shared memory with
+// coalesced, independent loads (the scan itself is a chain of T dependent steps: fed from global memory it cost
+// T x one DRAM latency, ~14 us for T = 20), one warp scans, all threads write the two output panels back.
+__global__ void __launch_bounds__(kVtThreads) vtrace_kernel(const VtraceParams p) {
+  extern __shared__ float vt_smem[];
+  const uint64_t col0 = (uint64_t)blockIdx.x * kVtCols;
+  const uint32_t ncol = (uint32_t)min((uint64_t)kVtCols, p.B - col0);
+  const uint32_t T = (uint32_t)p.T;
+  const uint32_t panel = T * kVtCols;
+  float* s_lr = vt_smem;            // log_rhos, later vs
+  float* s_d = s_lr + panel;        // discounts, later pg_advantages
+  float* s_r = s_d + panel;
+  float* s_v = s_r + panel;
+  for (uint32_t i = threadIdx.x; i < panel; i += kVtThreads) {
+    const uint32_t t = i / kVtCols, c = i - t * kVtCols;
+    if (c < ncol) {
+      const uint64_t g = (uint64_t)t * p.B + col0 + c;
+      s_lr[i] = p.log_rhos[g];
+      s_d[i] = p.discounts[g];
+      s_r[i] = p.rewards[g];
+      s_v[i] = p.values[g];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < ncol) {
+    const uint32_t c = threadIdx.x;
+    const float boot = p.bootstrap[col0 + c];
+    float acc = 0.f;        // vs_t - V(x_t), scanned backwards (vtrace.py:221-227)
+    float v_next = boot;    // V(x_{t+1})
+    float vs_next = boot;   // vs_{t+1}
+    for (uint32_t t = T; t-- > 0;) {
+      const uint32_t i = t * kVtCols + c;
+      const float rho = expf(s_lr[i]);
+      const float d = s_d[i], r = s_r[i], v = s_v[i];
+      const float crho = clamp_max(rho, p.clip_rho, p.has_clip_rho != 0);
+      const float cc = clamp_max(rho, 1.0f, true);
+      // deltas = clipped_rhos * (rewards + discounts * values_t_plus_1 - values)
+      const float delta = __fmul_rn(crho, __fsub_rn(__fadd_rn(r, __fmul_rn(d, v_next)), v));
+      // acc = deltas[t] + discounts[t] * cs[t] * acc
+      acc = __fadd_rn(delta, __fmul_rn(__fmul_rn(d, cc), acc));
+      const float vs = __fadd_rn(acc, v);
+      // pg_advantages = clipped_pg_rhos * (rewards + discounts * vs_t_plus_1 - values)
+      const float cpg = clamp_max(rho, p.clip_pg_rho, p.has_clip_pg_rho != 0);
+      s_d[i] = __fmul_rn(cpg, __fsub_rn(__fadd_rn(r, __fmul_rn(d, vs_next)), v));
+      s_lr[i] = vs;
+      v_next = v;
+      vs_next = vs;
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < panel; i += kVtThreads) {
+    const uint32_t t = i / kVtCols, c = i - t * kVtCols;
+    if (c < ncol) {
+      const uint64_t g = (uint64_t)t * p.B + col0 + c;
+      p.vs[g] = s_lr[i];
+      p.pg[g] = s_d[i];
+    }
+  }
+}
+
+// T too long for the shared-memory panels: one thread per column straight from global memory.
+__global__ void __launch_bounds__(128) vtrace_long_kernel(const VtraceParams p) {
   const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p.B) return;
   const float boot = p.bootstrap[j];
-  float acc = 0.f;        // vs_t - V(x_t), scanned backwards (vtrace.py:221-227)
-  float v_next = boot;    // V(x_{t+1})
-  float vs_next = boot;   // vs_{t+1}
+  float acc = 0.f, v_next = boot, vs_next = boot;
   for (uint64_t t = p.T; t-- > 0;) {
     const uint64_t i = t * p.B + j;
     const float rho = expf(p.log_rhos[i]);
     const float d = p.discounts[i], r = p.rewards[i], v = p.values[i];
     const float crho = clamp_max(rho, p.clip_rho, p.has_clip_rho != 0);
     const float c = clamp_max(rho, 1.0f, true);
-    // deltas = clipped_rhos * (rewards + discounts * values_t_plus_1 - values)
     const float delta = __fmul_rn(crho, __fsub_rn(__fadd_rn(r, __fmul_rn(d, v_next)), v));
-    // acc = deltas[t] + discounts[t] * cs[t] * acc
     acc = __fadd_rn(delta, __fmul_rn(__fmul_rn(d, c), acc));
     const float vs = __fadd_rn(acc, v);
-    // pg_advantages = clipped_pg_rhos * (rewards + discounts * vs_t_plus_1 - values)
     const float cpg = clamp_max(rho, p.clip_pg_rho, p.has_clip_pg_rho != 0);
     p.pg[i] = __fmul_rn(cpg, __fsub_rn(__fadd_rn(r, __fmul_rn(d, vs_next)), v));
     p.vs[i] = vs;
@@ -116,8 +175,12 @@ int mb_vtrace_f32(const float* log_rhos, const float* discounts, const float* re
   p.clip_pg_rho = clip_pg_rho;
   p.has_clip_rho = has_clip_rho;
   p.has_clip_pg_rho = has_clip_pg_rho;
-  const uint32_t threads = 128;
-  vtrace_kernel<<<(uint32_t)((B + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const size_t smem = (size_t)T * kVtCols * 4 * sizeof(float);
+  if (smem <= 40 * 1024) {
+    vtrace_kernel<<<(uint32_t)((B + kVtCols - 1) / kVtCols), kVtThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    vtrace_long_kernel<<<(uint32_t)((B + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  }
   MB_CUDA(cudaGetLastError());
   return 1;
 }

@@ -89,6 +89,12 @@ def test_vtrace_kernel_bit_exact_vs_torch_and_golden(golden_dir):
         assert _close(vs.cpu().numpy(), g[f"c{ci}_vs"]) and _close(pg.cpu().numpy(), g[f"c{ci}_pg"])
         ovs, opg = oracle.vtrace(*_inputs(ci, T, B), clip_rho=clip, clip_pg_rho=clip_pg)
         assert _close(vs.cpu().numpy(), ovs.astype(np.float64)) and _close(pg.cpu().numpy(), opg.astype(np.float64))
+    # a long unroll (T = 700: the global-memory variant of the kernel), ragged column count
+    ins = [torch.randn(700, 45, device="cuda") * 0.2, torch.full((700, 45), 0.97, device="cuda"),
+           torch.randn(700, 45, device="cuda"), torch.randn(700, 45, device="cuda"), torch.randn(45, device="cuda")]
+    vs, pg = moolib_b200.vtrace_from_importance_weights(*ins)
+    evs, epg = torch_vtrace(*ins, 1.0, 1.0)
+    assert torch.equal(vs, evs) and torch.equal(pg, epg)
     # the IMPALA learner's shape, extra trailing dimensions, NaN propagation through the clamps
     T, B = 20, 32
     ins = [torch.randn(T, B, 2, device="cuda") * 0.3, torch.full((T, B, 2), 0.99, device="cuda"),
