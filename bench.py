@@ -453,7 +453,12 @@ def run_ours(args):
             "gpu_launches": int(v["launches"]),
             "roofline": {"bound": "hbm", "kernel": f"Batcher.{dom_name} (dominant moolib_b200 op by device time in the step)",
                          "achieved": dom.get("achieved_gbs"), "peak": hbm, "unit": "GB/s", "frac": dom.get("frac"),
-                         "traffic": None,  # not measured in this run; see profiles/ for the ncu --set full capture
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the committed ncu --set full
+                         # capture (profiles/r02_ncu_gather_152MB.md: 152.30 MB read = the payload exactly, 101.79 MB written,
+                         # the rest of the writes is still in L2 at kernel end); algorithmic = 304.5 MB.  Not re-measured
+                         # in this run (a number taken under a profiler is never a bench value).
+                         "traffic": 254086656 if (args.envs == 256 and dom_name == "unroll_gather") else None,
+                         "traffic_source": "profiles/r02_ncu_gather_152MB.md",
                          "peak_kind": peak_kind, "per_op": ops, "aggregate_frac": ops.get("_all", {}).get("frac")},
             "roofline_nvlink": nvlink_roofline(v["ar"], world),
             "parity": parity,
