@@ -186,6 +186,10 @@ MB_API void* mb_ar_buffer(mb_ar_ctx* ctx, int slot, int ahead);
  * mb_ar_reduce_gated the HOST calls it once it has seen the round end with status MB_OK (a round that ended MB_AR_SHORT
  * reduced nothing and keeps accumulating into the same staging buffer).  All ranks advance together. */
 MB_API int mb_ar_slot_advance(mb_ar_ctx* ctx, int slot);
+/* What MB_AR_ALGO_AUTO resolves to for a message of `bytes` at this context's world size.  A host that wants the
+ * result IN PLACE -- flat_dst == mb_ar_buffer(ctx, slot, 0), possible with the two-shot algorithm only, whose all-gather
+ * leaves the reduced values in every rank's staging buffer: the kernel then skips its final local copy -- asks first. */
+MB_API int mb_ar_algo_for(mb_ar_ctx* ctx, uint64_t bytes);
 MB_API int mb_ar_world(mb_ar_ctx* ctx);
 MB_API int mb_ar_rank(mb_ar_ctx* ctx);
 

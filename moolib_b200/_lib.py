@@ -25,7 +25,7 @@ SYMBOLS = [
     "mb_gather_rows", "mb_stack_slot", "mb_cat_narrow", "mb_scatter_actions",
     "mb_ar_ctx_create", "mb_ar_ctx_destroy", "mb_ar_ctx_export", "mb_ar_ctx_import", "mb_ar_ctx_reset",
     "mb_ar_staging", "mb_ar_world", "mb_ar_rank", "mb_ar_stage", "mb_ar_allreduce", "mb_ar_result",
-    "mb_ar_flat_numel", "mb_ar_abort", "mb_ar_buffer", "mb_ar_slot_advance", "mb_ar_reduce_gated", "mb_ar_round_times", "mb_vtrace_f32", "mb_u8_to_f32", "mb_ar_xfer_pack", "mb_ar_xfer_unpack",
+    "mb_ar_flat_numel", "mb_ar_abort", "mb_ar_buffer", "mb_ar_slot_advance", "mb_ar_reduce_gated", "mb_ar_round_times", "mb_vtrace_f32", "mb_u8_to_f32", "mb_ar_xfer_pack", "mb_ar_xfer_unpack", "mb_ar_algo_for",
 ]
 
 
@@ -94,6 +94,7 @@ def load():
     L.mb_ar_flat_numel.argtypes = [ctypes.POINTER(u64), ci]
     L.mb_ar_flat_numel.restype = u64
     L.mb_ar_abort.argtypes = [vp]
+    L.mb_ar_algo_for.argtypes = [vp, u64]
     L.mb_ar_xfer_pack.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64), ci, vp]
     L.mb_ar_xfer_unpack.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(u64), ci, vp]
     L.mb_vtrace_f32.argtypes = [vp, vp, vp, vp, vp, ci, ctypes.c_float, ci, ctypes.c_float, u64, u64, vp, vp, vp]
@@ -278,6 +279,9 @@ class ArContext:
                                       "data": (int(self.buffer_ptr(slot, ahead)), False)}
         with torch.cuda.device(self.device):
             return torch.as_tensor(m, device=f"cuda:{self.device}")
+
+    def algo_for(self, nbytes):
+        return check(self.L.mb_ar_algo_for(self._ctx, nbytes))
 
     def advance(self, slot=0):
         check(self.L.mb_ar_slot_advance(self._ctx, slot))

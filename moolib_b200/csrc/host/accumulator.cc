@@ -42,6 +42,7 @@ struct ReduceSlot {
   cudaEvent_t event = nullptr;             // device path: completion of the K-A2 launch
   cudaEvent_t staged = nullptr;            // device path: this slot's gradients are complete (compute stream)
   bool kernelInFlight = false;
+  float* resultBase = nullptr;             // device gate: where K-A2 leaves the averaged gradients (flat layout)
   bool gated = false;                      // the in-flight launch is K-A0 + K-A2 (mb_ar_reduce_gated)
   Clock::time_point reduceStart;
   ~ReduceSlot() {
@@ -259,7 +260,7 @@ class Accumulator {
       torch::NoGradGuard ng;
       c10::cuda::CUDAGuard dg(device_);
       GradViews& av = viewsOf(accumBase(nextIndex_));
-      if (gradsAre(av) || (appliedSlot_ >= 0 && gradsAre(viewsOf(arena_->result[appliedSlot_].data_ptr<float>())))) {
+      if (gradsAre(av) || (appliedBase_ && gradsAre(viewsOf(appliedBase_)))) {
         // .grad shows an applied result (or is already accumulating): (back) to the accumulation buffer, zero-filled by
         // ONE memset of the flat buffer (reference: 36 zero_ launches, src/accumulator.cc:410-418)
         cudaMemsetAsync(av.base, 0, (size_t)arena_->total * 4, c10::cuda::getCurrentCUDAStream(device_).stream());
@@ -267,7 +268,7 @@ class Accumulator {
       } else {
         actuallyZeroGradients();
       }
-      appliedSlot_ = -1;
+      appliedBase_ = nullptr;
       return;
     }
     actuallyZeroGradients();
@@ -374,7 +375,7 @@ class Accumulator {
       }
     }
     arena_.reset();
-    appliedSlot_ = -1;
+    appliedBase_ = nullptr;
   }
 
   uint64_t flatBytes(const std::vector<torch::Tensor>& gs) {
@@ -495,9 +496,15 @@ class Accumulator {
     target->isCounting = true;
     target->gated = true;
     target->reduceStart = Clock::now();
+    // Two-shot (large gradient sets, N > 2): its all-gather leaves the averaged gradients in every rank's staging
+    // buffer, so the result is consumed IN PLACE (.grad will point at this ring position) and the kernel skips its
+    // final local copy.  One-shot writes the slot's separate result buffer (peers are still reading the staging).
+    const int algo = mb_ar_algo_for(reducer()->ctx(), (uint64_t)a.total * 4);
+    target->resultBase = algo == MB_AR_ALGO_TWOSHOT ? static_cast<float*>(mb_ar_buffer(reducer()->ctx(), (int)target->index, 0))
+                                                    : a.result[target->index].data_ptr<float>();
     launch_counter() += check(
         mb_ar_reduce_gated(reducer()->ctx(), (int)target->index, &target->data, virtualBatchSize_, nullptr, nullptr, 0,
-                           a.result[target->index].data_ptr<float>(), (uint64_t)a.total, /*scale=*/1, MB_AR_ALGO_AUTO,
+                           target->resultBase, (uint64_t)a.total, /*scale=*/1, algo,
                            (uint32_t)(parts_.rpc->getTimeout() * 1000), static_cast<mb_stream_t>(stream)),
         "Accumulator gated allreduce");
     cudaEventRecord(target->event, stream);
@@ -628,8 +635,8 @@ class Accumulator {
             recordTiming(*v, /*reduced=*/true);
             check(mb_ar_slot_advance(reducer()->ctx(), (int)v->index), "mb_ar_slot_advance");
             torch::NoGradGuard ng;
-            pointGradsAt(viewsOf(arena().result[v->index].data_ptr<float>()));
-            appliedSlot_ = (int)v->index;
+            pointGradsAt(viewsOf(v->resultBase));
+            appliedBase_ = v->resultBase;
           }
           finishReduce(v, total);
         }
@@ -1002,7 +1009,7 @@ class Accumulator {
       if (reducerReady_ && deviceGate() && gradsInArena()) {
         // new group epoch: the ring restarted at position 0; move .grad off whatever buffer it pointed at
         torch::NoGradGuard ng2;
-        appliedSlot_ = -1;
+        appliedBase_ = nullptr;
         repointForAccumulation();
       }
     }
@@ -1209,7 +1216,7 @@ class Accumulator {
   Clock::time_point deferredRequestSince_{};
   uint64_t nvlinkPublishes_ = 0, nvlinkFetches_ = 0;
   std::unique_ptr<GradArena> arena_;
-  int appliedSlot_ = -1;  // slot whose result buffer .grad currently shows (-1: none)
+  float* appliedBase_ = nullptr;  // the buffer of the applied result that .grad currently shows (null: none)
   struct RoundTiming {
     float gateUs, reduceUs;
     bool reduced;

@@ -149,6 +149,7 @@ struct ArParams {
   int32_t world;
   int32_t scale;
   int32_t force_u1;  // tuning aid: disable the U-way unrolled path
+  int32_t inplace;   // two-shot: the destination IS this rank's staging buffer (the all-gather already put it there)
   HostResult* result;
   const uint32_t* abort_flag;
   uint64_t timeout_ns;
@@ -589,19 +590,20 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_oneshot_kernel(const __grid_
   // Each block-iteration owns a contiguous chunk of U*512 vectors (U*8 KiB): thread t handles chunk[k*512 + t],
   // k < U, all U*NR peer loads in flight before the first add.  (Lanes must never be clamped to a common address:
   // thousands of threads loading one peer line serialise on NVLink -- measured 10x slowdowns.)
-  constexpr uint64_t kChunk = (uint64_t)U * kArThreads;
+  const uint32_t nthr = blockDim.x;  // 512, or 256 / 128 for small messages so that every SM gets a chunk
+  const uint64_t kChunk = (uint64_t)U * nthr;
   for (uint64_t base = (uint64_t)blockIdx.x * kChunk; base < p.total_vec; base += (uint64_t)gridDim.x * kChunk) {
     if (base + kChunk <= p.total_vec && !p.force_u1) {
       uint64_t v[U];
       float4 r[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) v[k] = base + (uint64_t)k * kArThreads + threadIdx.x;
+      for (int k = 0; k < U; ++k) v[k] = base + (uint64_t)k * nthr + threadIdx.x;
       reduce_vecs<NR, U>(p.stage, mask, v, r);  // mask == 0 -> zeros (src/accumulator.cc:426-428)
 #pragma unroll
       for (int k = 0; k < U; ++k) sink.put(v[k], scale_vec(r[k], s, do_scale));
     } else {
       const uint64_t cend = min(base + kChunk, p.total_vec);
-      for (uint64_t v0 = base + threadIdx.x; v0 < cend; v0 += kArThreads) {
+      for (uint64_t v0 = base + threadIdx.x; v0 < cend; v0 += nthr) {
         uint64_t v[1] = {v0};
         float4 r[1];
         reduce_vecs<NR, 1>(p.stage, mask, v, r);
@@ -625,7 +627,8 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
   const mb_ar_hdr tot = s_total;
   const bool do_scale = p.scale && tot.num_gradients != 0;
   const float s = reduce_scale(p, tot);
-  constexpr uint64_t kChunk = (uint64_t)U * kArThreads;
+  const uint32_t nthr = blockDim.x;
+  const uint64_t kChunk = (uint64_t)U * nthr;
   const uint64_t gstride = (uint64_t)gridDim.x * kChunk;
   // phase 1: reduce my slice and write it into every peer's staging (in place: slice `rank` of a peer's staging is
   // read only by me, and I overwrite an element only after I have loaded it) and into my own.  Chunks are relative
@@ -643,13 +646,13 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
         uint64_t v[U];
         float4 r[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) v[k] = sbase + cb + (uint64_t)k * kArThreads + threadIdx.x;
+        for (int k = 0; k < U; ++k) v[k] = sbase + cb + (uint64_t)k * nthr + threadIdx.x;
         reduce_vecs<NR, U>(p.stage, mask, v, r);
 #pragma unroll
         for (int k = 0; k < U; ++k) emit(v[k], r[k]);
       } else {
         const uint64_t cend = min(cb + kChunk, slen);
-        for (uint64_t j = cb + threadIdx.x; j < cend; j += kArThreads) {
+        for (uint64_t j = cb + threadIdx.x; j < cend; j += nthr) {
           uint64_t v[1] = {sbase + j};
           float4 r[1];
           reduce_vecs<NR, 1>(p.stage, mask, v, r);
@@ -660,6 +663,11 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
   }
   if (!block_barrier(p, true)) {
     report_failure(p);
+    return;
+  }
+  if (p.inplace) {
+    // the caller consumes the result from this rank's staging buffer itself: nothing left to move
+    write_result(p, tot);
     return;
   }
   // phase 2: every slice is now complete in my own staging (mine included, written by this same block before the
@@ -675,11 +683,11 @@ __global__ void __launch_bounds__(kArThreads, 1) ar_twoshot_kernel(const __grid_
       if (cb + kChunk <= slen) {
         float4 x[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) x[k] = ld_peer_f4(mine + (sbase + cb + (uint64_t)k * kArThreads + threadIdx.x) * 4);
+        for (int k = 0; k < U; ++k) x[k] = ld_peer_f4(mine + (sbase + cb + (uint64_t)k * nthr + threadIdx.x) * 4);
 #pragma unroll
-        for (int k = 0; k < U; ++k) sink.put(sbase + cb + (uint64_t)k * kArThreads + threadIdx.x, x[k]);
+        for (int k = 0; k < U; ++k) sink.put(sbase + cb + (uint64_t)k * nthr + threadIdx.x, x[k]);
       } else {
-        for (uint64_t j = cb + threadIdx.x; j < cend; j += kArThreads) sink.put(sbase + j, ld_peer_f4(mine + (sbase + j) * 4));
+        for (uint64_t j = cb + threadIdx.x; j < cend; j += nthr) sink.put(sbase + j, ld_peer_f4(mine + (sbase + j) * 4));
       }
     }
   }
@@ -897,6 +905,10 @@ int launch_reduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* cons
     if (algo == MB_AR_ALGO_TWOSHOT) twoshot = true;
     else if (algo == MB_AR_ALGO_AUTO) twoshot = total * 4 >= twoshot_min_bytes(ctx->world);
   }
+  if (!twoshot && ctx->world > 1 && flat_sink != nullptr && flat_sink == p.stage[ctx->rank]) {
+    set_error("mb_ar_allreduce: an in-place destination (this rank's staging) needs the two-shot algorithm");
+    return MB_EINVAL;
+  }
   const int sms = sm_count(ctx->device);
   if (sms <= 0) return MB_ECUDA;
   const uint64_t work_vec = twoshot ? p.slice_vec : p.total_vec;
@@ -908,21 +920,28 @@ int launch_reduce(mb_ar_ctx* ctx, int slot, const mb_ar_hdr* my_hdr, float* cons
   const uint64_t max_grid = std::min<uint64_t>((uint64_t)sms * blocks_per_sm, kArMaxBlocks);
   // Unroll: as many loads in flight per thread as fit (U*NR = 16), but never so coarse that SMs stay idle: a 4.4 MB
   // gradient set at U=8 is only 67 chunks -- 67 of 148 SMs pulling over NVLink.
+  // Few chunks (a 4.4 MB gradient set is a 0.55 MB slice per rank at N=8): shrink the CTAs before giving up SMs --
+  // 256- or 128-thread CTAs with one vector per thread keep all 148 SMs pulling over NVLink.
+  static const uint64_t env_threads = env_u64("MB_AR_THREADS", 0);
   int want_unroll = env_unroll ? (int)env_unroll : default_unroll(ctx->world);
+  uint32_t threads = env_threads ? (uint32_t)env_threads : (uint32_t)kArThreads;
+  auto chunks = [&](uint32_t thr, int u) { return (work_vec + (uint64_t)thr * u - 1) / ((uint64_t)thr * u); };
   if (!env_unroll)
-    while (want_unroll > 1 && (work_vec + (uint64_t)kArThreads * want_unroll - 1) / ((uint64_t)kArThreads * want_unroll) < max_grid)
-      want_unroll >>= 1;
+    while (want_unroll > 1 && chunks(threads, want_unroll) < max_grid) want_unroll >>= 1;
+  if (!env_threads)
+    while (threads > 128 && chunks(threads, want_unroll) < max_grid) threads >>= 1;
   int unroll = 1;
   ArKernel k = kernel_for(ctx->world, twoshot, want_unroll, &unroll);
-  const uint64_t chunk = (uint64_t)kArThreads * unroll;
+  const uint64_t chunk = (uint64_t)threads * unroll;
   uint64_t want = (work_vec + chunk - 1) / chunk;
   if (want == 0) want = 1;
   p.force_u1 = (int32_t)force_u1;
+  p.inplace = (twoshot && flat_sink != nullptr && flat_sink == p.stage[ctx->rank]) ? 1 : 0;
   const uint32_t grid = (uint32_t)std::min<uint64_t>(want, max_grid);
   const size_t smem = table_bytes(ntab);
   int rc = ensure_dyn_smem(reinterpret_cast<const void*>(k), smem);
   if (rc) return rc;
-  k<<<grid, kArThreads, smem, stream>>>(p);
+  k<<<grid, threads, smem, stream>>>(p);
   MB_CUDA(cudaGetLastError());
   if (timed) {
     MB_CUDA(cudaEventRecord(ctx->ev[slot][2], stream));
@@ -1158,6 +1177,11 @@ int mb_ar_slot_advance(mb_ar_ctx* ctx, int slot) {
   std::lock_guard<std::mutex> l(ctx->mu);
   ctx->parity[slot] = (ctx->parity[slot] + 1) % kBufs;
   return MB_OK;
+}
+
+int mb_ar_algo_for(mb_ar_ctx* ctx, uint64_t bytes) {
+  if (!ctx) return MB_EINVAL;
+  return (ctx->world > 1 && bytes >= twoshot_min_bytes(ctx->world)) ? MB_AR_ALGO_TWOSHOT : MB_AR_ALGO_ONESHOT;
 }
 
 int mb_ar_world(mb_ar_ctx* ctx) { return ctx ? ctx->world : MB_EINVAL; }

@@ -200,3 +200,32 @@ def test_publish_region_roundtrip(n):
         assert (ring == 3.0).all().item()
     finally:
         w.close()
+
+
+@pytest.mark.parametrize("n", [m for m in WORLDS if m >= 2])
+def test_twoshot_in_place_result(n):
+    """Two-shot with flat_dst == the rank's own staging buffer: the all-gather already left the averaged values there,
+    the kernel skips its final copy; one-shot refuses an in-place destination (peers would still be reading it)."""
+    numel = 700_001
+    total = _lib.flat_numel([numel])
+    w = World(n, total * 4)
+    try:
+        ins = [np.concatenate([gen_input(77 + r, [numel], "f32"), np.zeros(total - numel, np.float32)]) for r in range(n)]
+        bufs = []
+        for r in range(n):
+            with torch.cuda.device(r):
+                b = w.ctx[r].buffer(total)
+                b.copy_(torch.from_numpy(ins[r]))
+                bufs.append(b)
+        launch_all(w, lambda r: w.ctx[r].reduce_gated(1, flat_dst=bufs[r], hdr=(1, 0, 4, 1), algo=_lib.MB_AR_ALGO_TWOSHOT))
+        exact, eh = oracle.allreduce_rankorder(ins, [(1, 0, 4)] * n)
+        for r in range(n):
+            assert w.ctx[r].result() == (eh, 0)
+            assert bufs[r].cpu().numpy().tobytes() == exact.tobytes(), r
+        with torch.cuda.device(0):
+            with pytest.raises(_lib.MoolibB200Error, match="in-place destination"):
+                w.ctx[0].reduce_gated(1, flat_dst=bufs[0], algo=_lib.MB_AR_ALGO_ONESHOT)
+        assert w.ctx[0].algo_for(4096) == _lib.MB_AR_ALGO_ONESHOT
+        assert w.ctx[0].algo_for(64 << 20) == (_lib.MB_AR_ALGO_TWOSHOT if n > 2 else _lib.MB_AR_ALGO_ONESHOT)
+    finally:
+        w.close()

@@ -12,6 +12,7 @@ ap.add_argument("--algos", default="oneshot,twoshot")
 ap.add_argument("--iters", type=int, default=30)
 ap.add_argument("--world", type=int, default=0)
 ap.add_argument("--tag", default="")
+ap.add_argument("--inplace", type=int, default=1, help="two-shot: consume the result in the staging buffer (what the Accumulator does)")
 a = ap.parse_args()
 n = a.world or torch.cuda.device_count()
 ALG = {"oneshot": _lib.MB_AR_ALGO_ONESHOT, "twoshot": _lib.MB_AR_ALGO_TWOSHOT, "auto": _lib.MB_AR_ALGO_AUTO}
@@ -34,7 +35,8 @@ for size in [int(x) for x in a.sizes.split(",")]:
         for it in range(a.iters + 5):
             for r in range(n):
                 with torch.cuda.device(r):
-                    ctx[r].reduce_gated(1, flat_dst=dst[r], hdr=(1, 0, 1, 1), scale=False, algo=ALG[algo])
+                    d = ctx[r].buffer(numel, ahead=0) if (algo == "twoshot" and a.inplace) else dst[r]
+                    ctx[r].reduce_gated(1, flat_dst=d, hdr=(1, 0, 1, 1), scale=False, algo=ALG[algo])
             for r in range(n):
                 torch.cuda.synchronize(r)
             ok = all(ctx[r].result()[1] == 0 for r in range(n))
@@ -42,7 +44,8 @@ for size in [int(x) for x in a.sizes.split(",")]:
             if it == 0:
                 exp = float(n * (n + 1) // 2)
                 # two-shot writes the reduced values back into the staging: re-fill before the next round
-                assert all((dst[r] == exp).all().item() for r in range(n)), (size, algo)
+                outs = [ctx[r].buffer(numel, ahead=0) if (algo == "twoshot" and a.inplace) else dst[r] for r in range(n)]
+                assert all((outs[r] == exp).all().item() for r in range(n)), (size, algo)
             ts = [ctx[r].round_times() for r in range(n)]
             if it >= 5:
                 red.append(max(t[1] for t in ts))
@@ -53,7 +56,7 @@ for size in [int(x) for x in a.sizes.split(",")]:
         red.sort(); gate.sort()
         med = red[len(red) // 2]
         bus = size * 2 * (n - 1) / n / med / 1e3 if n > 1 else 0
-        print(json.dumps({"tag": a.tag, "n": n, "bytes": size, "algo": algo, "reduce_us_p50": round(med, 2),
+        print(json.dumps({"tag": a.tag, "n": n, "bytes": size, "algo": algo + ("(in place)" if algo == "twoshot" and a.inplace else ""), "reduce_us_p50": round(med, 2),
                           "p10": round(red[len(red) // 10], 2), "p90": round(red[len(red) * 9 // 10], 2),
                           "gate_us_p50": round(gate[len(gate) // 2], 2), "busbw_gbs": round(bus, 1),
                           "algbw_gbs": round(size / med / 1e3, 1)}), flush=True)
