@@ -589,7 +589,7 @@ class Accumulator {
     if (v->countOp && v->countOp->future->done()) {
       auto op = std::move(v->countOp);
       v->countOp.reset();
-      ran = true;
+      // the slot keeps its turn: the count only opens (or not) the gate, the round ends with the reduction's result
       Bytes value;
       const int flags = op->future->snapshot(&value, nullptr);  // no lock held while we start the next operation
       if (flags & 1) {
@@ -824,6 +824,9 @@ class Accumulator {
         if (requestedViaNvlink_.count(n) && nvlinkSyncPossible()) {
           if (publishPending_.empty()) viaNvl.push_back(n);
           else later.push_back(n);
+        } else if (requestedViaNvlink_.count(n) && gradsOnCuda_ && !nvlinkOff_ && !reducerReady_ &&
+                   now - epochStart_ < std::chrono::seconds(5)) {
+          later.push_back(n);  // the requester is connected for this epoch, this peer not quite yet: next tick
         } else {
           viaTcp.push_back(n);
         }
@@ -1041,6 +1044,7 @@ class Accumulator {
       isFindingLeader_ = true;
       isWaitingForModel_ = false;
       requestDeferred_ = false;
+      epochStart_ = now;
       hasGradients_ = false;
       reducerReady_ = false;
       members_.clear();
@@ -1213,7 +1217,7 @@ class Accumulator {
     return e && *e == '0';
   }();
   bool requestDeferred_ = false;
-  Clock::time_point deferredRequestSince_{};
+  Clock::time_point deferredRequestSince_{}, epochStart_ = Clock::now();
   uint64_t nvlinkPublishes_ = 0, nvlinkFetches_ = 0;
   std::unique_ptr<GradArena> arena_;
   float* appliedBase_ = nullptr;  // the buffer of the applied result that .grad currently shows (null: none)
