@@ -327,8 +327,32 @@ std::shared_ptr<PyFuture> DeviceReducerSet::allReduceTensor(const std::string& n
   fut->ready = std::move(pyTensor);  // in place, like the reference (test/test_reduce.py:56)
   fut->keep = op;
   fut->progress = [op] { op->step(); };
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    std::weak_ptr<TensorReduceOp> weak = op;  // the future keeps the operation alive; a dropped future ends it
+    pending_.push_back([weak] {
+      auto o = weak.lock();
+      if (!o) return true;
+      o->step();
+      return o->phase == 3;
+    });
+  }
   op->step();
   return fut;
+}
+
+void DeviceReducerSet::progressAll() {
+  std::vector<std::function<bool()>> work;
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    if (pending_.empty()) return;
+    work.swap(pending_);
+  }
+  std::vector<std::function<bool()>> keep;
+  for (auto& f : work)
+    if (!f()) keep.push_back(std::move(f));
+  std::lock_guard<std::mutex> l(mu_);
+  for (auto& f : keep) pending_.push_back(std::move(f));
 }
 
 }  // namespace mbh

@@ -71,6 +71,8 @@ class DeviceReducerSet {
   std::shared_ptr<DeviceReducer> get(const std::string& tag, int device, uint64_t maxBytes, int nslots);
   // group.all_reduce(name, cuda_tensor): in-place sum over the members (A8)
   std::shared_ptr<PyFuture> allReduceTensor(const std::string& name, torch::Tensor t, py::object pyTensor);
+  // advance every device all_reduce of this group that is still in flight (called from Group.update())
+  void progressAll();
 
  private:
   std::shared_ptr<GroupService> service_;
@@ -78,6 +80,7 @@ class DeviceReducerSet {
   std::mutex mu_;
   std::map<std::string, std::shared_ptr<DeviceReducer>> reducers_;
   std::map<std::string, std::weak_ptr<FutureState>> inflight_;  // all_reduce on CUDA tensors, by operation name
+  std::vector<std::function<bool()>> pending_;                   // step functions; true = finished
 };
 
 struct GroupParts {

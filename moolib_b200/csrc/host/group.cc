@@ -794,6 +794,10 @@ struct PyGroup {
     reducers = std::make_shared<DeviceReducerSet>(service, info);
   }
   bool update() {
+    // device-side all_reduces advance here too, not only when their own future is polled: a loop that waits on one
+    // future (all(f.done() for f in futures) stops at the first unfinished one) must not starve the operations the
+    // peers are waiting for
+    reducers->progressAll();
     py::gil_scoped_release nogil;
     return service->update(*info, sortOrder, timeoutMs);
   }
