@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--settle", type=int, default=24,
+                    help="untimed optimizer steps in front of the W warm-up steps of each arm: the caching allocator "
+                         "(152 MB unroll buffers), cuDNN's autotuner and the actor/learner queues reach their steady state; "
+                         "lock-step learners stall on ANY rank's cudaMalloc, so N ranks see N times the hiccups")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=256)
     ap.add_argument("--max-seconds", type=float, default=150.0, help="wall-time bound of the reference / cpu legs")
@@ -314,7 +318,7 @@ def run_ours(args):
 
     service["fn"] = pump
     hbm, peak_kind = measured_peaks()
-    K, W = args.steps, args.warmup
+    K, W, S = args.steps, args.warmup, max(0, args.settle)
     results = {}
     timer = BatchOpTimer(torch, _C.kernel_launches)
 
@@ -355,7 +359,7 @@ def run_ours(args):
             if os.environ.get("BENCH_DEBUG"):
                 print(f"[rank {rank}] {mode} step {n} t={time.time() % 1000:.2f} actor={res.actor_steps}",
                       file=sys.stderr, flush=True)
-            if n == W:
+            if n == S + W:
                 torch.cuda.synchronize()
                 barrier()
                 if sampler:
@@ -370,9 +374,9 @@ def run_ours(args):
                 state["step_t"] = [state["t0"]]
                 start_evt.record()
                 return True
-            if state.get("t0") is not None and n < W + K:
+            if state.get("t0") is not None and n < S + W + K:
                 state["step_t"].append(time.perf_counter())
-            if n == W + K:
+            if n == S + W + K:
                 end_evt.record()
                 dbg(f"{mode}: end recorded, synchronizing")
                 torch.cuda.synchronize()
@@ -439,7 +443,7 @@ def run_ours(args):
         # H2D per optimizer step: actor steps per optimizer step x one [B] observation slab; D2H: the grad-norm read
         actor_per_step = e["actor_steps"] / max(K, 1)
         line = {
-            "metric": METRIC, "value": round(v["value"], 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": round(v["value"], 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "settle_steps": S,
             "ms_per_step": round(v["ms"] / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "IMPALA vtrace learner loop (examples/impala.py), synthetic 84x84x4 u8 obs, "
