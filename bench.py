@@ -12,16 +12,22 @@ grad-norm clipping.  One process = one learner = one GPU; a "step" is one optimi
 frames/s = unroll_length * batch_size * optimizer_steps / s, the reference's own env_train_steps definition
 (examples/vtrace/experiment.py:155,207-211), summed over all N learners.
 
-Two timed regions of exactly K steps each (after W warm-up steps each), barrier + cuda synchronize on both sides,
-CUDA events, max over ranks:
+Before anything is timed, two CHECKED reductions run through the public Accumulator on the real 36-tensor gradient
+layout (rank r contributes r+1, then randn(seed=r)): every rank's result must equal the CPU oracle bit for bit and all
+ranks must hold identical bits -- the `"parity"` object of the JSON line; a mismatch ends the run with exit code 3.
+
+Two timed regions of exactly K steps each (after --settle untimed steady-state steps and W warm-up steps each), barrier +
+cuda synchronize on both sides, CUDA events, max over ranks:
   value : observations already resident in HBM, no host reads inside the loop
   e2e   : observations arrive in pinned host slabs (the EnvPool result format) and are copied H2D every actor step,
           the grad-norm is read back to the host every optimizer step (as experiment.py:166 does) -- through the
           public moolib API (Batcher / Accumulator).
 Both go through moolib_b200's Batcher (copy kernels) and Accumulator (stage + NVLink allreduce kernels).
-`roofline` is the batch copy kernel (the dominant moolib_b200 kernel by bytes), timed with CUDA events around every
-Batcher launch inside the `value` region.  Successive launches touch different buffers (T=21 x 256 envs x 28 KB =
-152 MB per time batch, > L2), so inputs are larger than L2 (config.l2 says so).
+`roofline` is the dominant moolib_b200 kernel family by device time inside the `value` region (the UnrollBatcher gather:
+one launch per unroll), timed with CUDA events around every Batcher launch; `per_op` lists all of them and their
+aggregate.  `roofline_nvlink` is K-A2 inside the same region, timed by the allreduce context's own CUDA events on the
+reduce stream (K-A0 = the wait for the slowest peer is reported separately).  Successive launches touch different
+buffers (T=21 x 256 envs x 28 KB = 152 MB per unroll, > L2), so inputs are larger than L2 (config.l2 says so).
 
 `--impl reference` runs the UNMODIFIED reference (oracle/_ref, compiled from /root/reference by oracle/build_ref.sh)
 through the same loop on the host cores (device "cpu": its Batcher / Accumulator / RPC allreduce are CPU code and so is

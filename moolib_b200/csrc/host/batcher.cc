@@ -633,15 +633,10 @@ class UnrollBatcher {
         j.dst_pitch = T_ * B_ * inner;
         for (int64_t t = 0; t < T_; ++t) {
           const torch::Tensor& src = held_[(size_t)t][i];
-          const uint8_t ok = srcOk_[(size_t)t * L + i];
-          if (ok) {
-            if (j.row_bytes == 0) continue;
-            j.src = src.data_ptr();
-            j.dst = static_cast<char*>(big[i].data_ptr()) + t * B_ * inner;
-            q_.add(j, ok == 2, dev);
-          } else {
-            big[i].select(1, t).copy_(src.view(big[i].select(1, t).sizes()), /*non_blocking=*/true);
-          }
+          if (j.row_bytes == 0) continue;
+          j.src = src.data_ptr();
+          j.dst = static_cast<char*>(big[i].data_ptr()) + t * B_ * inner;
+          q_.add(j, srcOk_[(size_t)t * L + i] == 2, dev);  // alignedOk(): every source is kernel-readable
         }
       }
       for (int64_t k = 0; k < K; ++k) {
