@@ -71,12 +71,52 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md), read through NVML from a thread of this
+    process every 100 ms.  (Round 1 ran `nvidia-smi -lms 200` as a child process: its queries, and the fork of this
+    process that started it, showed up as 5-30 ms hiccup steps in the arm it was sampling.)  Falls back to nvidia-smi
+    when NVML cannot be loaded."""
+
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.rows, self.proc, self.thread, self.stop_flag = gpu_index, [], None, None, threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self._sample()  # the first query initialises driver state: keep it out of the timed region
+            self.rows.clear()
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.rows.append((sm, mx, {name for name, const in self.REASONS if mask & getattr(n, const, 0)}))
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -89,22 +129,27 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        names = [n for n, _ in self.REASONS]
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((int(float(r[0])), int(float(r[1])),
+                                  {n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")}))
+            except Exception:
+                pass
 
     def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        sm = sorted(r[0] for r in self.rows)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            reasons |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[1] for r in self.rows), default=None),
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 class BatchOpTimer:
