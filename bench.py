@@ -514,6 +514,10 @@ def run_ours(args):
                          # in this run (a number taken under a profiler is never a bench value).
                          "traffic": 254086656 if (args.envs == 256 and dom_name == "unroll_gather") else None,
                          "traffic_source": "profiles/r02_ncu_gather_152MB.md",
+                         "note": "in-loop figure: the gather's sources are the actor's last 21 step outputs (152 MB > L2 in "
+                                 "total, the most recent ones may still be L2-resident, hence a fraction that can read "
+                                 "slightly above 1); isolated and L2-flushed the same launch runs at 0.82 of the measured "
+                                 "peak (profiles/r02_sweep_batch_stack_1gpu.jsonl)",
                          "peak_kind": peak_kind, "per_op": ops, "aggregate_frac": ops.get("_all", {}).get("frac")},
             "roofline_nvlink": nvlink_roofline(v["ar"], world),
             "parity": parity,
