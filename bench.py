@@ -54,10 +54,11 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=8)
-    ap.add_argument("--settle", type=int, default=24,
-                    help="untimed optimizer steps in front of the W warm-up steps of each arm: the caching allocator "
-                         "(152 MB unroll buffers), cuDNN's autotuner and the actor/learner queues reach their steady state; "
-                         "lock-step learners stall on ANY rank's cudaMalloc, so N ranks see N times the hiccups")
+    ap.add_argument("--settle", type=int, default=56,
+                    help="untimed optimizer steps in front of the W warm-up steps of each arm: the learner-batch queue fills "
+                         "to its cap over ~3 unroll cycles (~40 steps) and until then every cycle makes the caching allocator "
+                         "cudaMalloc another set of 152 MB unroll buffers (a device-synchronising call); cuDNN's autotuner "
+                         "settles too.  Lock-step learners stall on ANY rank's hiccup, so N ranks see N times as many")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=256)
     ap.add_argument("--max-seconds", type=float, default=150.0, help="wall-time bound of the reference / cpu legs")
