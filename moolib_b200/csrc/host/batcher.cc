@@ -237,6 +237,21 @@ class CopyQueue {
   }
 };
 
+// Jobs that were described but not launched (an exception on the way) must not survive into the next call: their
+// sources may be gone by then.
+struct LaunchGuard {
+  CopyQueue& q;
+  bool launched = false;
+  explicit LaunchGuard(CopyQueue& queue) : q(queue) {}
+  void launch() {
+    q.launch();
+    launched = true;
+  }
+  ~LaunchGuard() {
+    if (!launched) q.discard();
+  }
+};
+
 // How one leaf of an item sits inside its batch tensor, in bytes.  `outer` rows; one index of the batch dimension is
 // `inner` bytes; the batch tensor holds `dstCount` indices per row.
 struct LeafGeom {
@@ -346,8 +361,9 @@ class Batcher {
       cat_ = false;
       fill_ = 0;
     }
+    LaunchGuard guard(q_);
     for (size_t i = 0; i < leaves_.size(); ++i) addStackCopy(q_, out_[i], geom_[i], dim_, fill_, leaves_[i], itemSizes_[i]);
-    q_.launch();
+    guard.launch();
     leaves_.clear();
     if (++fill_ == size_) return close();
     return {};
@@ -378,6 +394,7 @@ class Batcher {
               "dimension (" + std::to_string(dim_) + "). Got " + std::to_string(n) + " and " + std::to_string(t.size(dim_)));
       }
       int64_t taken = 0;
+      LaunchGuard guard(q_);
       while (true) {
         if (!open_) {
           out_.clear();
@@ -403,7 +420,7 @@ class Batcher {
         if (fill_ == size_) finished.push_back(close());
         if (taken >= n) break;
       }
-      q_.launch();
+      guard.launch();
       leaves_.clear();
     }
     for (auto& r : finished) emit(std::move(r));
@@ -602,6 +619,20 @@ class UnrollBatcher {
               "dimension (" + std::to_string(catDim_) + "). Got " + std::to_string(n) + " and " + std::to_string(t.size(catDim_)));
       }
     }
+    // an exception below (allocation failure, set_extra on a non-dict item, ...) abandons this unroll cleanly
+    struct Abandon {
+      UnrollBatcher& u;
+      bool done = false;
+      ~Abandon() {
+        if (done) return;
+        u.q_.discard();
+        u.held_.clear();
+        u.extra_.reset();
+        u.out_.clear();
+        u.xout_.clear();
+        u.open_ = false;
+      }
+    } abandon{*this};
     // what the kernels may read directly, decided once per (step, leaf) -- not once per piece
     const size_t L = first.size();
     srcOk_.assign((size_t)T_ * L, 0);
@@ -678,7 +709,8 @@ class UnrollBatcher {
       taken += take;
       if (fill_ == B_) finished.push_back(closeBatch());
     }
-    q_.launch();  // ONE launch for the whole unroll: T x leaves x learner batches pitched copies
+    q_.launch();  // ONE launch for the whole unroll: T x leaves (x pieces) pitched copies
+    abandon.done = true;
     held_.clear();
     extra_.reset();
   }

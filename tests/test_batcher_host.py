@@ -215,3 +215,25 @@ def test_to_device_cpu_is_identity_nest():
     nest = {"a": torch.arange(4), "b": (torch.ones(2), "s")}
     out = moolib_b200.to_device(nest, "cpu")
     assert _same_nest(out, nest) and out["b"][1] == "s"
+
+
+def test_failed_calls_leave_no_stale_work_behind():
+    """An item that fails half-way (ATen refuses a leaf after other leaves were already described) must not leave copies
+    queued for the next call, and an UnrollBatcher that cannot finish an unroll starts the next one cleanly."""
+    b = moolib_b200.Batcher(size=2, dim=0)
+    b.stack({"a": torch.zeros(3), "b": torch.zeros(4)})
+    with pytest.raises(RuntimeError):
+        b.stack({"a": torch.ones(3), "b": torch.ones(5)})  # leaf b: shape mismatch inside copy_
+    b.stack({"a": torch.full((3,), 2.0), "b": torch.full((4,), 2.0)})
+    out = b.get()
+    assert out["a"][1].eq(2).all() and out["b"][1].eq(2).all()
+    ub = moolib_b200.UnrollBatcher(2, 2, "cpu")
+    ub.set_extra("k", (torch.zeros(1, 4),))
+    ub.stack([torch.zeros(4)])
+    with pytest.raises(RuntimeError, match="set_extra needs dict items"):
+        ub.stack([torch.ones(4)])
+    assert ub.empty()
+    for v in (3.0, 4.0):
+        ub.stack([torch.full((4,), v)])
+    got = [ub.get(), ub.get()]
+    assert ub.empty() and all(g[0].shape == (2, 2) and g[0][0].eq(3).all() and g[0][1].eq(4).all() for g in got)
