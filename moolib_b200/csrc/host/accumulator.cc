@@ -887,7 +887,8 @@ class Accumulator {
     }
   }
 
-  void commitModelUpdate() {
+  // Returns false when the update could not be applied and was requested again.
+  bool commitModelUpdate() {
     MBH_PHASE("commitModelUpdate");
     torch::NoGradGuard ng;
     std::vector<Bytes> ps, bs;
@@ -895,10 +896,26 @@ class Accumulator {
     bool viaNvlink = false;
     {
       std::lock_guard<std::mutex> nl(netMu_);
+      viaNvlink = newViaNvlink_;
+    }
+    if (viaNvlink && !nvlinkSyncPossible()) {
+      // the NVLink context of this epoch went away between the request and the answer: drop the update and ask again
+      // (the new request carries the current capability, i.e. the model then comes over the control plane)
+      {
+        std::lock_guard<std::mutex> nl(netMu_);
+        haveNewParameters_ = false;
+        newParameters_.clear();
+        newBuffers_.clear();
+        newUserState_.clear();
+      }
+      requestModel();
+      return false;
+    }
+    {
+      std::lock_guard<std::mutex> nl(netMu_);
       haveNewParameters_ = false;
       haveNewBuffers_ = false;
       modelVersion_ = newModelVersion_;
-      viaNvlink = newViaNvlink_;
       ps.swap(newParameters_);
       bs.swap(newBuffers_);
       state.swap(newUserState_);
@@ -908,7 +925,6 @@ class Accumulator {
     if (bs.size() != buffers_.size()) throw std::runtime_error("Model buffers size mismatch in update!");
     if (viaNvlink) {
       // pull the leader's publish region straight into the parameter / buffer tensors: ONE launch of P2P loads
-      if (!nvlinkSyncPossible()) throw std::runtime_error("moolib_b200: NVLink model update without a connected context");
       auto it = std::find(members_.begin(), members_.end(), syncLeader_);
       if (it == members_.end()) throw std::runtime_error("moolib_b200: model update from a leader outside the group");
       std::vector<float*> ptrs;
@@ -945,6 +961,7 @@ class Accumulator {
     userState_ = pickleLoads(state);
     hasNewUserState_ = true;
     hasReceivedModel_ = true;
+    return true;
   }
 
   void commitBuffersUpdate() {
@@ -1085,10 +1102,7 @@ class Accumulator {
         ignore = !isWaitingForModel_ && modelVersion_ != newModelVersion_;
         if (ignore) haveNewParameters_ = false;
       }
-      if (!ignore) {
-        commitModelUpdate();
-        isWaitingForModel_ = false;
-      }
+      if (!ignore && commitModelUpdate()) isWaitingForModel_ = false;
     } else if (isWaitingForModel_ && now - isWaitingForModelTimestamp_ >= std::chrono::seconds(60)) {
       requestModel();
     } else if (!isWaitingForModel_ && connectedImpl() && syncLeader_ != myName_ &&
